@@ -1,0 +1,265 @@
+// Element-wise / segment kernels of the GET hot path and the library bookkeeping.
+#include <stdarg.h>
+#include <atomic>
+
+#include "common.cuh"
+
+namespace getb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- GGNN backward, element-wise stage (reference forward Models/BiDAF/wrapper.py:194-206)
+__global__ void __launch_bounds__(256) ggnn_gate_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z,
+                                                            const float* __restrict__ h, const float* __restrict__ x,
+                                                            int64_t numel, float* __restrict__ dhp,
+                                                            float* __restrict__ dzp, float* __restrict__ dx, int vec) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= numel) return;
+  float d[4], zz[4], hh[4], xx[4], o0[4], o1[4], o2[4];
+  const int nvalid = (int)min((int64_t)4, numel - i);
+  if (vec) {
+    float4 a = *reinterpret_cast<const float4*>(dout + i); d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+    a = *reinterpret_cast<const float4*>(z + i); zz[0] = a.x; zz[1] = a.y; zz[2] = a.z; zz[3] = a.w;
+    a = *reinterpret_cast<const float4*>(h + i); hh[0] = a.x; hh[1] = a.y; hh[2] = a.z; hh[3] = a.w;
+    a = *reinterpret_cast<const float4*>(x + i); xx[0] = a.x; xx[1] = a.y; xx[2] = a.z; xx[3] = a.w;
+  } else {
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = e < nvalid;
+      d[e] = ok ? dout[i + e] : 0.f; zz[e] = ok ? z[i + e] : 0.f; hh[e] = ok ? h[i + e] : 0.f; xx[e] = ok ? x[i + e] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    o0[e] = d[e] * zz[e] * (1.0f - hh[e] * hh[e]);
+    o1[e] = d[e] * (hh[e] - xx[e]) * zz[e] * (1.0f - zz[e]);
+    o2[e] = d[e] * (1.0f - zz[e]);
+  }
+  if (vec) {
+    *reinterpret_cast<float4*>(dhp + i) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+    *reinterpret_cast<float4*>(dzp + i) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<float4*>(dx + i) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+  } else {
+    for (int e = 0; e < nvalid; ++e) { dhp[i + e] = o0[e]; dzp[i + e] = o1[e]; dx[i + e] = o2[e]; }
+  }
+}
+
+// ---- column sums (bias gradients): stage 1 = per-chunk partial sums, stage 2 = fixed-order reduction
+constexpr int COLSUM_ROWS = 256;  // rows per stage-1 block
+__global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* __restrict__ a, int64_t ld, int M, int N,
+                                                            float* __restrict__ part) {
+  // block (bx, by): columns bx*32..+31, rows by*COLSUM_ROWS..; 8 warps each stride the rows, lanes = columns
+  __shared__ float s[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * COLSUM_ROWS;
+  const int r1 = min(M, r0 + COLSUM_ROWS);
+  float acc = 0.f;
+  if (n < N)
+    for (int r = r0 + warp; r < r1; r += 8) acc += __ldg(a + (int64_t)r * ld + n);
+  s[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s[w][lane];
+    part[(int64_t)blockIdx.y * N + n] = v;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ part, int nparts, int N,
+                                                            float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float v = 0.f;
+  for (int q = 0; q < nparts; ++q) v += part[(int64_t)q * N + n];
+  out[n] = v;
+}
+
+// ---- row gather / scatter / segment sum (reference basic_fc_model.py:80-121 without the Python loops)
+__global__ void __launch_bounds__(256) rows_copy_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                        const int32_t* __restrict__ idx, int R, int W,
+                                                        float* __restrict__ out, int64_t ld_out, int scatter) {
+  const int r = blockIdx.x;
+  const int64_t srow = scatter ? r : idx[r];
+  const int64_t drow = scatter ? idx[r] : r;
+  const float* s = src + srow * ld_src;
+  float* d = out + drow * ld_out;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) d[c] = s[c];
+}
+
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                          const int32_t* __restrict__ offsets, int W,
+                                                          float* __restrict__ out, int64_t ld_out) {
+  const int sgm = blockIdx.x;
+  const int r0 = offsets[sgm], r1 = offsets[sgm + 1];
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float v = 0.f;
+    for (int r = r0; r < r1; ++r) v += src[(int64_t)r * ld_src + c];
+    out[(int64_t)sgm * ld_out + c] = v;
+  }
+}
+
+// ---- claim read-out: masked mean over nodes (reference graph_based_semantic_structure.py:145-153)
+__global__ void __launch_bounds__(256) masked_mean_fwd_kernel(const float* __restrict__ h, const int64_t* __restrict__ ids,
+                                                              const int64_t* __restrict__ lens, int N, int H,
+                                                              float* __restrict__ out) {
+  const int g = blockIdx.x;
+  const float len = (float)lens[g];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float v = 0.f;
+    for (int i = 0; i < N; ++i)
+      if (ids[(int64_t)g * N + i] > 0) v += h[((int64_t)g * N + i) * H + c];
+    out[(int64_t)g * H + c] = v / len;
+  }
+}
+__global__ void __launch_bounds__(256) masked_mean_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ ids,
+                                                              const int64_t* __restrict__ lens, int N, int H,
+                                                              float* __restrict__ dh) {
+  const int g = blockIdx.x / N, i = blockIdx.x % N;
+  const float len = (float)lens[g];
+  const bool on = ids[(int64_t)g * N + i] > 0;
+  for (int c = threadIdx.x; c < H; c += blockDim.x)
+    dh[((int64_t)g * N + i) * H + c] = on ? dout[(int64_t)g * H + c] / len : 0.f;
+}
+
+__global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, int64_t numel, uint32_t thr,
+                                                           float scale, uint32_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < numel) out[i] = drop_keep(seed, (uint64_t)i, thr) ? scale : 0.f;
+}
+
+// ---- mean cross-entropy + dlogits (reference losses.py:29-32); one warp, B is a few hundred at most
+__global__ void __launch_bounds__(32) cross_entropy_kernel(const float* __restrict__ logits,
+                                                           const int64_t* __restrict__ labels, int B, int C,
+                                                           float* __restrict__ loss, float* __restrict__ dlogits) {
+  const int lane = threadIdx.x;
+  float total = 0.f;
+  const float invB = 1.0f / (float)B;
+  for (int b = lane; b < B; b += 32) {
+    const float* row = logits + (int64_t)b * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, row[c]);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+    const float lse = mx + logf(sum);
+    const int y = (int)labels[b];
+    total += lse - row[y];
+    if (dlogits)
+      for (int c = 0; c < C; ++c) dlogits[(int64_t)b * C + c] = (expf(row[c] - lse) - (c == y ? 1.f : 0.f)) * invB;
+  }
+  // fixed-order reduction over lanes for run-to-run determinism
+  __shared__ float s[32];
+  s[lane] = total;
+  __syncwarp();
+  if (lane == 0) {
+    float v = 0.f;
+    for (int l = 0; l < 32; ++l) v += s[l];
+    *loss = v * invB;
+  }
+}
+
+}  // namespace getb
+
+using namespace getb;
+
+extern "C" int get_ggnn_gate_bwd_f32(const float* dout, const float* z, const float* h, const float* x, int64_t numel,
+                                     float* dhp, float* dzp, float* dx, void* stream) {
+  GETB_REQUIRE(dout && z && h && x && dhp && dzp && dx, "get_ggnn_gate_bwd_f32: null pointer");
+  if (numel <= 0) return 0;
+  const int vec = (numel % 4 == 0) && aligned16(dout) && aligned16(z) && aligned16(h) && aligned16(x) &&
+                  aligned16(dhp) && aligned16(dzp) && aligned16(dx);
+  ggnn_gate_bwd_kernel<<<ceil_div((numel + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(dout, z, h, x, numel, dhp,
+                                                                                         dzp, dx, vec);
+  GETB_CHECK_LAUNCH("get_ggnn_gate_bwd_f32");
+  return 0;
+}
+
+extern "C" int64_t get_colsum_workspace_floats(int M, int N) {
+  return (int64_t)ceil_div(M > 0 ? M : 1, COLSUM_ROWS) * (N > 0 ? N : 1);
+}
+
+extern "C" int get_colsum_f32(const float* a, int64_t ld, int M, int N, float* out, float* workspace, void* stream) {
+  GETB_REQUIRE(a && out && workspace, "get_colsum_f32: null pointer");
+  GETB_REQUIRE(M > 0 && N > 0, "get_colsum_f32: bad sizes");
+  const int nparts = ceil_div(M, COLSUM_ROWS);
+  dim3 grid(ceil_div(N, 32), nparts);
+  colsum_stage1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, ld, M, N, workspace);
+  GETB_CHECK_LAUNCH("get_colsum_f32/stage1");
+  colsum_stage2_kernel<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(workspace, nparts, N, out);
+  GETB_CHECK_LAUNCH("get_colsum_f32/stage2");
+  return 0;
+}
+
+extern "C" int get_rows_gather_f32(const float* src, int64_t ld_src, const int32_t* idx, int R, int W, float* out,
+                                   int64_t ld_out, void* stream) {
+  GETB_REQUIRE(src && idx && out, "get_rows_gather_f32: null pointer");
+  if (R <= 0 || W <= 0) return 0;
+  rows_copy_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, R, W, out, ld_out, 0);
+  GETB_CHECK_LAUNCH("get_rows_gather_f32");
+  return 0;
+}
+
+extern "C" int get_rows_scatter_f32(const float* src, int64_t ld_src, const int32_t* idx, int R, int W, float* out,
+                                    int64_t ld_out, void* stream) {
+  GETB_REQUIRE(src && idx && out, "get_rows_scatter_f32: null pointer");
+  if (R <= 0 || W <= 0) return 0;
+  rows_copy_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, R, W, out, ld_out, 1);
+  GETB_CHECK_LAUNCH("get_rows_scatter_f32");
+  return 0;
+}
+
+extern "C" int get_segment_sum_f32(const float* src, int64_t ld_src, const int32_t* offsets, int S, int W, float* out,
+                                   int64_t ld_out, void* stream) {
+  GETB_REQUIRE(src && offsets && out, "get_segment_sum_f32: null pointer");
+  if (S <= 0 || W <= 0) return 0;
+  segment_sum_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(src, ld_src, offsets, W, out, ld_out);
+  GETB_CHECK_LAUNCH("get_segment_sum_f32");
+  return 0;
+}
+
+extern "C" int get_masked_mean_fwd_f32(const float* h, const int64_t* ids, const int64_t* lens, int G, int N, int H,
+                                       float* out, void* stream) {
+  GETB_REQUIRE(h && ids && lens && out, "get_masked_mean_fwd_f32: null pointer");
+  if (G <= 0) return 0;
+  masked_mean_fwd_kernel<<<G, 256, 0, (cudaStream_t)stream>>>(h, ids, lens, N, H, out);
+  GETB_CHECK_LAUNCH("get_masked_mean_fwd_f32");
+  return 0;
+}
+
+extern "C" int get_masked_mean_bwd_f32(const float* dout, const int64_t* ids, const int64_t* lens, int G, int N, int H,
+                                       float* dh, void* stream) {
+  GETB_REQUIRE(dout && ids && lens && dh, "get_masked_mean_bwd_f32: null pointer");
+  if (G <= 0) return 0;
+  masked_mean_bwd_kernel<<<G * N, 256, 0, (cudaStream_t)stream>>>(dout, ids, lens, N, H, dh);
+  GETB_CHECK_LAUNCH("get_masked_mean_bwd_f32");
+  return 0;
+}
+
+extern "C" int get_dropout_mask_f32(float* out, int64_t numel, float p, uint32_t seed, void* stream) {
+  GETB_REQUIRE(out && p >= 0.f && p < 1.f, "get_dropout_mask_f32: bad arguments");
+  if (numel <= 0) return 0;
+  dropout_mask_kernel<<<ceil_div(numel, 256), 256, 0, (cudaStream_t)stream>>>(out, numel, drop_threshold(p),
+                                                                             1.0f / (1.0f - p), seed);
+  GETB_CHECK_LAUNCH("get_dropout_mask_f32");
+  return 0;
+}
+
+extern "C" int get_cross_entropy_f32(const float* logits, const int64_t* labels, int B, int C, float* loss,
+                                     float* dlogits, void* stream) {
+  GETB_REQUIRE(logits && labels && loss && B > 0 && C > 0, "get_cross_entropy_f32: bad arguments");
+  cross_entropy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(logits, labels, B, C, loss, dlogits);
+  GETB_CHECK_LAUNCH("get_cross_entropy_f32");
+  return 0;
+}
+
+extern "C" int get_b200_abi_version(void) { return GET_B200_ABI_VERSION; }
+extern "C" const char* get_b200_last_error(void) { return g_err; }
+extern "C" int64_t get_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

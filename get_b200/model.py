@@ -1,0 +1,173 @@
+"""`Graph_basedSemantiStructure`: drop-in for the reference GET model
+(Models/FCWithEvidences/graph_based_semantic_structure.py:15-274, base classes
+Models/FCWithEvidences/basic_fc_model.py:14-121 and Models/base_model.py:144-197).
+
+Same constructor dict, same `forward(query, document, verbose=False, **kargs)` / `predict`, same
+`state_dict()` keys and shapes (incl. the inert `bilstm.*`, `query_bilstm.*`, `trans.*`), so it loads and
+writes the reference's checkpoints and can be constructed by MasterFC/master_get.py:145 unchanged.
+All per-claim Python loops and host syncs of the reference (`_pad_left_tensor`, `_pad_right_tensor`, the GSL
+mask loop) are replaced by segment index arithmetic on the device.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .keywords import KeyWordSettings
+from .modules import GGNN, GGNN_with_GSL, LSTM, ConcatNotEqualSelfAtt, Linear
+
+
+def _init_weights(m):
+    """torch_utils.init_weights (reference torch_utils.py:379-388): Xavier-uniform weight, zero bias."""
+    if type(m) == nn.Linear:
+        nn.init.xavier_uniform_(m.weight)
+        if hasattr(m.bias, "data"):
+            m.bias.data.fill_(0)
+
+
+class Graph_basedSemantiStructure(nn.Module):
+    def __init__(self, params):
+        super().__init__()
+        self._params = params
+        # Models/base_model.py:147-162 (writes the embedding dims back into the dict)
+        if isinstance(params["embedding"], np.ndarray):
+            params["embedding_input_dim"] = params["embedding"].shape[0]
+            params["embedding_output_dim"] = params["embedding"].shape[1]
+            self.embedding = nn.Embedding.from_pretrained(embeddings=torch.Tensor(params["embedding"]),
+                                                          freeze=params["embedding_freeze"])
+        else:
+            self.embedding = nn.Embedding(num_embeddings=params["embedding_input_dim"],
+                                          embedding_dim=params["embedding_output_dim"])
+        self.num_classes = params["num_classes"]
+        self.fixed_length_right = params["fixed_length_right"]
+        self.fixed_length_left = params["fixed_length_left"]
+        self.use_claim_source = params["use_claim_source"]
+        self.use_article_source = params["use_article_source"]
+        self._use_cuda = params["cuda"]
+        self.num_att_heads_for_words = params["num_att_heads_for_words"]
+        self.num_att_heads_for_evds = params["num_att_heads_for_evds"]
+        self.dropout_gnn = params["dropout_gnn"]
+        self.dropout_left = params["dropout_left"]
+        self.dropout_right = params["dropout_right"]
+        self.hidden_size = params["hidden_size"]
+        self.output_size = params["output_size"]
+        self.gsl_rate = params["gsl_rate"]
+        if self.use_claim_source:
+            self.claim_source_embs = nn.Embedding.from_pretrained(
+                embeddings=torch.Tensor(params["claim_source_embeddings"]), freeze=False)
+            self.claim_emb_size = params["claim_source_embeddings"].shape[1]
+        if self.use_article_source:
+            self.article_source_embs = nn.Embedding.from_pretrained(
+                embeddings=torch.Tensor(params["article_source_embeddings"]), freeze=False)
+            self.article_emb_size = params["article_source_embeddings"].shape[1]
+        D = params["embedding_output_dim"]
+        H = self.hidden_size
+        # inert parameters of the base class (basic_fc_model.py:49-52), kept for checkpoint compatibility
+        self.bilstm = LSTM(input_size=D, hidden_size=H, num_layers=1, bidirectional=True, batch_first=True,
+                           dropout=self.dropout_left)
+        self.query_bilstm = LSTM(input_size=D, hidden_size=H, num_layers=1, bidirectional=True, batch_first=True,
+                                 dropout=self.dropout_right)
+        self.ggnn4claim_1 = GGNN(in_features=D, out_features=H)                                   # gbss.py:52
+        self.ggnn_with_gsl = GGNN_with_GSL(input_dim=D, hidden_dim=H, output_dim=H, rate=self.gsl_rate,
+                                           dropout=self.dropout_gnn)                             # gbss.py:54
+        self.trans = Linear(2 * H, H)                                                             # gbss.py:55 (never called)
+        self.self_att_word = ConcatNotEqualSelfAtt(inp_dim=2 * H, out_dim=H,
+                                                   num_heads=self.num_att_heads_for_words)       # gbss.py:223-233
+        evd_in = H + self.num_att_heads_for_words * H
+        if self.use_claim_source:
+            evd_in += self.claim_emb_size
+        if self.use_article_source:
+            evd_in += self.article_emb_size
+        self.self_att_evd = ConcatNotEqualSelfAtt(inp_dim=evd_in, out_dim=H,
+                                                  num_heads=self.num_att_heads_for_evds)         # gbss.py:235-249
+        evd_input_size = H
+        if self.use_claim_source:
+            evd_input_size += self.claim_emb_size
+        evd_input_size += H * self.num_att_heads_for_words * self.num_att_heads_for_evds
+        if self.use_article_source:
+            evd_input_size += self.article_emb_size * self.num_att_heads_for_evds
+        self.out = nn.Sequential(nn.Linear(evd_input_size, H), nn.Linear(H, self.output_size))   # gbss.py:69-72
+        self.out[0].apply(_init_weights)
+        self.out[1].apply(_init_weights)
+        self.dropout_seeds = None   # tests: dict(claim=, feat_prop1=, word_scorer1=, feat_prop2=) fixed seeds
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _segments(evd_cnt: torch.Tensor, b1: int, n: int):
+        """Device-side index arithmetic replacing the per-claim loops of basic_fc_model.py:80-121.
+        Returns seg_of_row (B1,), slot_of_row (B1,) = claim*n + j, offsets (B+1,), all int32. No host sync:
+        B1 is known from the shape of the flattened evidence tensor."""
+        cnt = evd_cnt.to(torch.int64)
+        B = cnt.shape[0]
+        offsets = torch.zeros((B + 1,), dtype=torch.int64, device=cnt.device)
+        offsets[1:] = torch.cumsum(cnt, 0)
+        seg = torch.repeat_interleave(torch.arange(B, device=cnt.device), cnt, output_size=b1)
+        slot = seg * n + (torch.arange(b1, device=cnt.device) - offsets[seg])
+        return seg.to(torch.int32), slot.to(torch.int32), offsets.to(torch.int32)
+
+    def forward(self, query: torch.Tensor, document: torch.Tensor, verbose=False, **kargs):
+        K = KeyWordSettings
+        assert K.Query_lens in kargs and K.Doc_lens in kargs
+        assert query.size(0) == document.size(0)
+        batch_size, n, R = document.size()
+        assert n == 30 or n == kargs.get(K.FIXED_NUM_EVIDENCES, 30)   # gbss.py:93 hard-codes 30
+        _, _, d_lens = kargs[K.DocLensIndices]
+        assert K.DocContentNoPaddingEvidence in kargs
+        doc = kargs[K.DocContentNoPaddingEvidence]                       # (B1, R)
+        b1 = doc.size(0)
+        assert d_lens.shape[0] == b1
+        doc_adj = kargs[K.Evd_Docs_Adj]
+        evd_cnt = kargs[K.EvidenceCountPerQuery]
+        assert evd_cnt.size(0) == batch_size
+        seeds = self.dropout_seeds or {}
+        seg, slot, offsets = self._segments(evd_cnt, b1, n)
+        emb_fused = not self.embedding.weight.requires_grad
+
+        # claim graph -> masked mean (gbss.py:144-155)
+        q_adj = kargs[K.Query_Adj]
+        if emb_fused:
+            q_hid = self.ggnn4claim_1(q_adj, table=self.embedding.weight, ids=query, seed=seeds.get("claim"))
+        else:
+            q_hid = self.ggnn4claim_1(q_adj, self.embedding(query.long()), seed=seeds.get("claim"))
+        q_claim = ops.MaskedMeanFn.apply(q_hid, query, kargs[K.Query_lens])           # (B, H)
+        query_repr = ops.SegmentExpandFn.apply(q_claim, seg, offsets)                # (B1, H)
+
+        # evidence graphs (gbss.py:107)
+        blk_seeds = None
+        if seeds:
+            blk_seeds = (seeds.get("feat_prop1", 0), seeds.get("word_scorer1", 0), seeds.get("feat_prop2", 0))
+        if emb_fused:
+            doc_out = self.ggnn_with_gsl(doc_adj, table=self.embedding.weight, ids=doc, seeds=blk_seeds)
+        else:
+            doc_out = self.ggnn_with_gsl(doc_adj, self.embedding(doc.long()), seeds=blk_seeds)
+
+        # word-level attention (gbss.py:110, 173-193)
+        avg, word_att = self.self_att_word(query_repr, doc_out, doc >= 1)
+        avg = torch.flatten(avg, start_dim=1)                                        # (B1, H*heads), index d*heads+head
+
+        # evidence-level attention (gbss.py:113-119, 195-221)
+        if self.use_claim_source:
+            claim_embs = self.claim_source_embs(kargs[K.QuerySources].long()).squeeze(1)   # (B, E_c)
+            new_left = torch.cat([claim_embs, q_claim], dim=-1)      # == _pad_right(_pad_left(.))[:, 0, :]
+        else:
+            new_left = q_claim
+        extra = None
+        if self.use_article_source:
+            src = kargs[K.DocSources]
+            src = src.masked_fill(src == -1, 0)
+            extra = self.article_source_embs(src.long()).reshape(batch_size * n, -1)
+        padded = ops.SegmentPadFn.apply(avg, slot, batch_size * n, extra).view(batch_size, n, -1)
+        evd_mask = torch.sum(document, dim=-1) >= 1
+        att_avg, evd_att = self.self_att_evd(new_left, padded, evd_mask)
+        final = torch.cat([new_left, torch.flatten(att_avg, start_dim=1)], dim=-1)   # gbss.py:264-267
+        hid = ops.linear(final, self.out[0].weight, self.out[0].bias)                # gbss.py:121
+        phi = ops.linear(hid, self.out[1].weight, self.out[1].bias)
+        if kargs.get(K.OutputRankingKey, False):
+            return phi, (word_att, evd_att)
+        return phi
+
+    def predict(self, query: torch.Tensor, doc: torch.Tensor, verbose: bool = False, **kargs):
+        """gbss.py:269-274"""
+        self.train(False)
+        assert query.size(0) == doc.size(0)
+        return self(query, doc, **kargs)

@@ -1,0 +1,541 @@
+"""Host-side wrappers over the C-ABI (raw device pointers in, nothing allocated natively) and the
+`torch.autograd.Function`s the drop-in modules are built from.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every arithmetic step of the
+hot path is a kernel of libget_b200.so. Nothing in this file falls back to torch math when the library or a
+GPU is missing -- the calls raise.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_DGATE_R, EPI_DROPOUT_OUT, EPI_SIGMOID, EPI_STORE, EPI_TANH, EPI_TANH_BLEND,
+                   EPI_TANH_ROWGROUP, GemmDesc)
+
+_SM_COUNT = 148
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError("get_b200: %s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("get_b200: %s must be float32, got %s" % (name, t.dtype))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Raw(object):
+    """Explicit GEMM operand (used for the embedding table addressed through a row gather, whose logical
+    (M, K) extent is larger than the table itself)."""
+    __slots__ = ("ptr", "ld", "trans", "shape")
+
+    def __init__(self, ptr, ld, trans, shape):
+        self.ptr, self.ld, self.trans, self.shape = ptr, ld, trans, tuple(shape)
+
+    def t(self):
+        return Raw(self.ptr, self.ld, 1 - self.trans, self.shape[::-1])
+
+
+def _operand(t, name: str):
+    """2-D logical (i, k) tensor view -> (ptr, ld, trans)."""
+    if isinstance(t, Raw):
+        return t.ptr, t.ld, t.trans
+    _chk_f32(t, name)
+    assert t.dim() == 2, name
+    s0, s1 = t.stride()
+    if t.shape[1] == 1 or s1 == 1:
+        return t.data_ptr(), (s0 if t.shape[0] > 1 else max(s0, t.shape[1])), 0
+    if t.shape[0] == 1 or s0 == 1:
+        return t.data_ptr(), s1, 1
+    raise RuntimeError("get_b200.gemm: operand %s has no unit stride %s" % (name, (t.stride(),)))
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1)
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def new_seed() -> int:
+    """32-bit dropout seed drawn from torch's CPU generator (follows torch.manual_seed)."""
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
+def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tensor, *, epilogue: int = EPI_STORE,
+         bias0=None, bias1=None, aux0=None, aux1=None, out1=None, group_rows: int = 0, alpha: float = 1.0,
+         accumulate: bool = False, rowidx: Optional[torch.Tensor] = None, drop_p: float = 0.0, drop_seed: int = 0,
+         drop_cols: int = 0, drop_out_p: float = 0.0, drop_out_seed: int = 0, split_k: Optional[int] = None):
+    """out[m,n] = epilogue(sum_s A_s[m,:] . B_s[n,:]); A_s logical (M,K_s), B_s logical (N,K_s)."""
+    lib = _lib.load()
+    M, N = out.shape
+    d = GemmDesc()
+    d.nseg = len(segments)
+    ktiles = 0
+    for s, (a, b) in enumerate(segments):
+        ks = a.shape[1]
+        assert a.shape[0] == M and b.shape[0] == N and b.shape[1] == ks, (a.shape, b.shape, out.shape)
+        d.A[s].ptr, d.A[s].ld, d.A[s].trans = _operand(a, "A%d" % s)
+        d.B[s].ptr, d.B[s].ld, d.B[s].trans = _operand(b, "B%d" % s)
+        d.K[s] = ks
+        ktiles += (ks + 15) // 16
+    if rowidx is not None:
+        assert rowidx.dtype == torch.int64 and rowidx.is_cuda and rowidx.is_contiguous()
+        d.A[0].rowidx = rowidx.data_ptr()
+    _chk_f32(out, "C")
+    d.M, d.N, d.C, d.ldc = M, N, out.data_ptr(), _ld(out)
+    d.alpha, d.accumulate, d.epilogue = alpha, int(accumulate), epilogue
+    for name, t in (("bias0", bias0), ("bias1", bias1)):
+        if t is not None:
+            _chk_f32(t, name)
+            assert t.numel() == N and t.is_contiguous()
+            setattr(d, name, t.data_ptr())
+    for name, t in (("aux0", aux0), ("aux1", aux1), ("out1", out1)):
+        if t is not None:
+            _chk_f32(t, name)
+            setattr(d, name, t.data_ptr())
+            setattr(d, "ld_" + name, _ld(t))
+    d.group_rows = group_rows
+    d.drop_p, d.drop_seed, d.drop_cols = drop_p, drop_seed & 0xFFFFFFFF, drop_cols
+    d.drop_out_p, d.drop_out_seed = drop_out_p, drop_out_seed & 0xFFFFFFFF
+    if split_k is None:
+        tiles = ((M + 127) // 128) * ((N + 63) // 64)
+        split_k = 1
+        if tiles < _SM_COUNT and ktiles >= 16:
+            split_k = max(1, min(ktiles // 8, (2 * _SM_COUNT + tiles - 1) // tiles))
+    ws = None
+    if split_k > 1:
+        ws = torch.empty((split_k * M * N,), dtype=torch.float32, device=out.device)
+        d.workspace = ws.data_ptr()
+    d.split_k = split_k
+    _lib.check(lib.get_gemm_f32(C.byref(d), _stream()), "get_gemm_f32")
+    return out
+
+
+def graph_aggregate(adj, x, keep=None, out=None, transpose=False, accumulate=False):
+    lib = _lib.load()
+    _chk_f32(adj, "adj"); _chk_f32(x, "x")
+    G, N, H = x.shape
+    assert adj.shape == (G, N, N) and adj.is_contiguous() and x.is_contiguous()
+    if out is None:
+        assert not accumulate
+        out = torch.empty_like(x)
+    if keep is not None:
+        assert keep.dtype == torch.uint8 and keep.shape == (G, N) and keep.is_contiguous()
+    _lib.check(lib.get_graph_aggregate_f32(adj.data_ptr(), x.data_ptr(), _ptr(keep), out.data_ptr(), G, N, H,
+                                           int(transpose), int(accumulate), _stream()), "get_graph_aggregate_f32")
+    return out
+
+
+def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, want_score=True):
+    """Fused scorer -> top-k -> refined aggregation. Returns (score (G,N) | None, keep (G,N) uint8, out (G,N,H))."""
+    lib = _lib.load()
+    _chk_f32(adj, "adj"); _chk_f32(feat, "feat"); _chk_f32(wp, "wp"); _chk_f32(gate, "gate")
+    G, N, H = feat.shape
+    assert adj.shape == (G, N, N) and adj.is_contiguous() and feat.is_contiguous()
+    assert wp.numel() == H and wp.is_contiguous() and gate.numel() == 12 and gate.is_contiguous()
+    score = torch.empty((G, N), dtype=torch.float32, device=feat.device) if want_score else None
+    keep = torch.empty((G, N), dtype=torch.uint8, device=feat.device)
+    out = torch.empty_like(feat)
+    _lib.check(lib.get_gsl_fused_f32(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, int(k),
+                                     float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF,
+                                     _ptr(score), keep.data_ptr(), out.data_ptr(), _stream()), "get_gsl_fused_f32")
+    return score, keep, out
+
+
+def gsl_mask_adj(adj, score, k):
+    lib = _lib.load()
+    _chk_f32(adj, "adj"); _chk_f32(score, "score")
+    G, N, _ = adj.shape
+    adj = adj.contiguous()
+    score = score.reshape(G, N).contiguous()
+    out = torch.empty_like(adj)
+    keep = torch.empty((G, N), dtype=torch.uint8, device=adj.device)
+    _lib.check(lib.get_gsl_mask_adj_f32(adj.data_ptr(), score.data_ptr(), G, N, int(k), out.data_ptr(),
+                                        keep.data_ptr(), _stream()), "get_gsl_mask_adj_f32")
+    return out, keep
+
+
+def dropout_mask(numel: int, p: float, seed: int, device) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty((numel,), dtype=torch.float32, device=device)
+    _lib.check(lib.get_dropout_mask_f32(out.data_ptr(), numel, float(p), seed & 0xFFFFFFFF, _stream()),
+               "get_dropout_mask_f32")
+    return out
+
+
+def colsum(a2d: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk_f32(a2d, "a")
+    M, N = a2d.shape
+    out = torch.empty((N,), dtype=torch.float32, device=a2d.device)
+    ws = torch.empty((int(lib.get_colsum_workspace_floats(M, N)),), dtype=torch.float32, device=a2d.device)
+    _lib.check(lib.get_colsum_f32(a2d.data_ptr(), _ld(a2d), M, N, out.data_ptr(), ws.data_ptr(), _stream()),
+               "get_colsum_f32")
+    return out
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """(G,P,D) -> (G*P, D) view with a uniform row stride (copies only if the layout forbids it)."""
+    G, P, D = t.shape
+    if t.stride(2) == 1 and t.stride(0) == P * t.stride(1):
+        return t.as_strided((G * P, D), (t.stride(1), 1), t.storage_offset())
+    return t.contiguous().view(G * P, D)
+
+
+# =================================================================================================
+# GGNN layer (reference Models/BiDAF/wrapper.py:174-208; backward per SURVEY.md Appendix A.1)
+# =================================================================================================
+class GGNNLayerFn(torch.autograd.Function):
+    """out = GGNN(adj', x_in).  x_in is either `feat` (G,N,Din) or rows `ids` (G,N) of the frozen `table`.
+    keep (G,N) uint8 restricts the adjacency to edges with a kept endpoint (GSL); pre_agg = adj' @ drop(x_in)
+    (from the fused GSL kernel) replaces the aggregation of the projected features by linearity."""
+
+    @staticmethod
+    def forward(ctx, adj, feat, table, ids, keep, pre_agg, p_drop, seed,
+                Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1):
+        G, N = adj.shape[0], adj.shape[1]
+        M = G * N
+        H, Din = Wp.shape
+        dev = adj.device
+        adj = adj.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        x = torch.empty((M, H), **f32)
+        drop = dict(drop_p=p_drop, drop_seed=seed, drop_cols=Din) if p_drop > 0 else {}
+        if feat is not None:
+            feat2d = _rows2d(feat)
+            gemm([(feat2d, Wp)], x, **drop)
+            rowidx = None
+        else:
+            rowidx = ids.reshape(-1).to(torch.int64).contiguous()
+            # logical A = table rows gathered by rowidx; shape bookkeeping through an expanded view
+            _chk_f32(table, "table")
+            a_view = Raw(table.data_ptr(), table.stride(0), 0, (M, Din))
+            gemm([(a_view, Wp)], x, rowidx=rowidx, **drop)
+        a = torch.empty((M, H), **f32)
+        if pre_agg is not None:
+            gemm([(_rows2d(pre_agg), Wp)], a)
+        else:
+            graph_aggregate(adj, x.view(G, N, H), keep, out=a.view(G, N, H))
+        z = torch.empty((M, H), **f32)
+        r = torch.empty((M, H), **f32)
+        rx = torch.empty((M, H), **f32)
+        h = torch.empty((M, H), **f32)
+        out = torch.empty((M, H), **f32)
+        gemm([(a, Wz0), (x, Wz1)], z, epilogue=EPI_SIGMOID, bias0=bz0, bias1=bz1)
+        gemm([(a, Wr0), (x, Wr1)], r, epilogue=EPI_SIGMOID, bias0=br0, bias1=br1, aux0=x, out1=rx)
+        gemm([(a, Wh0), (rx, Wh1)], out, epilogue=EPI_TANH_BLEND, bias0=bh0, bias1=bh1, aux0=z, aux1=x, out1=h)
+        ctx.save_for_backward(adj, feat, table, rowidx, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1)
+        ctx.p_drop, ctx.seed, ctx.dims = p_drop, seed, (G, N, H, Din)
+        return out.view(G, N, H)
+
+    @staticmethod
+    def backward(ctx, dout):
+        adj, feat, table, rowidx, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1 = ctx.saved_tensors
+        G, N, H, Din = ctx.dims
+        M = G * N
+        dev = dout.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        dout = dout.contiguous().view(M, H)
+        dhp = torch.empty((M, H), **f32)
+        dzp = torch.empty((M, H), **f32)
+        drp = torch.empty((M, H), **f32)
+        dx = torch.empty((M, H), **f32)
+        da = torch.empty((M, H), **f32)
+        _lib.check(lib.get_ggnn_gate_bwd_f32(dout.data_ptr(), z.data_ptr(), h.data_ptr(), x.data_ptr(), M * H,
+                                             dhp.data_ptr(), dzp.data_ptr(), dx.data_ptr(), _stream()),
+                   "get_ggnn_gate_bwd_f32")
+        # d(rx) = dhp @ Wh1 ; drp = d(rx)*x*r*(1-r) ; dx += d(rx)*r
+        gemm([(dhp, Wh1.t())], drp, epilogue=EPI_DGATE_R, aux0=x, aux1=r, out1=dx)
+        # da = dhp@Wh0 + dzp@Wz0 + drp@Wr0
+        gemm([(dhp, Wh0.t()), (dzp, Wz0.t()), (drp, Wr0.t())], da)
+        # dx += dzp@Wz1 + drp@Wr1 + adj'^T @ da
+        gemm([(dzp, Wz1.t()), (drp, Wr1.t())], dx, accumulate=True)
+        graph_aggregate(adj, da.view(G, N, H), keep, out=dx.view(G, N, H), transpose=True, accumulate=True)
+        need = ctx.needs_input_grad
+        grads = [None] * 21
+
+        def wgrad(dg, act):
+            w = torch.empty((H, H), **f32)
+            gemm([(dg.t(), act.t())], w)
+            return w
+
+        # order of inputs: ... 8:Wp 9:Wz0 10:bz0 11:Wz1 12:bz1 13:Wr0 14:br0 15:Wr1 16:br1 17:Wh0 18:bh0 19:Wh1 20:bh1
+        if need[9]: grads[9] = wgrad(dzp, a)
+        if need[11]: grads[11] = wgrad(dzp, x)
+        if need[13]: grads[13] = wgrad(drp, a)
+        if need[15]: grads[15] = wgrad(drp, x)
+        if need[17]: grads[17] = wgrad(dhp, a)
+        if need[19]: grads[19] = wgrad(dhp, rx)
+        if need[10] or need[12]:
+            g = colsum(dzp)
+            grads[10] = g if need[10] else None
+            grads[12] = g if need[12] else None
+        if need[14] or need[16]:
+            g = colsum(drp)
+            grads[14] = g if need[14] else None
+            grads[16] = g if need[16] else None
+        if need[18] or need[20]:
+            g = colsum(dhp)
+            grads[18] = g if need[18] else None
+            grads[20] = g if need[20] else None
+        drop = dict(drop_p=ctx.p_drop, drop_seed=ctx.seed, drop_cols=Din) if ctx.p_drop > 0 else {}
+        if need[8]:
+            # dWp^T (Din,H) = Xd^T @ dx  (gather + dropout are applied on the A operand)
+            wT = torch.empty((Din, H), **f32)
+            if feat is not None:
+                gemm([(_rows2d(feat).t(), dx.t())], wT, **drop)
+            else:
+                a_view = Raw(table.data_ptr(), table.stride(0), 0, (M, Din))
+                gemm([(a_view.t(), dx.t())], wT, rowidx=rowidx, **drop)
+            grads[8] = wT.t()
+        if feat is not None and need[1]:
+            dfeat = torch.empty((M, Din), **f32)
+            if ctx.p_drop > 0:
+                gemm([(dx, Wp.t())], dfeat, epilogue=EPI_DROPOUT_OUT, drop_out_p=ctx.p_drop, drop_out_seed=ctx.seed)
+            else:
+                gemm([(dx, Wp.t())], dfeat)
+            grads[1] = dfeat.view(G, N, Din)
+        return tuple(grads)
+
+
+def ggnn_layer(adj, feat, table, ids, keep, pre_agg, p_drop, seed, params: Sequence[torch.Tensor]):
+    return GGNNLayerFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params)
+
+
+# =================================================================================================
+# ConcatNotEqualSelfAtt / MultiHeadSelfAttentionICLR2017Extend
+# (reference thirdparty/two_branches_attention.py:121-148, thirdparty/self_attention.py:75-100)
+# =================================================================================================
+class ConcatAttFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, left, right, mask_u8, W1, W2):
+        lib = _lib.load()
+        G, P, Dr = right.shape
+        H = W1.shape[0]
+        X = W1.shape[1] - Dr
+        Cn = W2.shape[0]
+        dev = right.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        right2d = _rows2d(right)
+        W1 = W1.contiguous()
+        W2 = W2.contiguous()
+        t = torch.empty((G * P, H), **f32)
+        if left is not None:
+            lp = torch.empty((G, H), **f32)
+            gemm([(left.contiguous(), W1[:, :X])], lp)
+            gemm([(right2d, W1[:, X:])], t, epilogue=EPI_TANH_ROWGROUP, aux0=lp, group_rows=P)
+        else:
+            gemm([(right2d, W1)], t, epilogue=EPI_TANH)
+        att = torch.empty((G, P, Cn), **f32)
+        pooled = torch.empty((G, Dr, Cn), **f32)
+        mask_u8 = mask_u8.contiguous()
+        _lib.check(lib.get_att_pool_fwd_f32(t.data_ptr(), right2d.data_ptr(), _ld(right2d), W2.data_ptr(),
+                                            mask_u8.data_ptr(), G, P, H, Dr, Cn, att.data_ptr(), pooled.data_ptr(),
+                                            Dr * Cn, _stream()), "get_att_pool_fwd_f32")
+        ctx.save_for_backward(left, right2d, W1, W2, t, att)
+        ctx.dims = (G, P, H, Dr, Cn, X)
+        return pooled, att
+
+    @staticmethod
+    def backward(ctx, d_pooled, d_att):
+        lib = _lib.load()
+        left, right2d, W1, W2, t, att = ctx.saved_tensors
+        G, P, H, Dr, Cn, X = ctx.dims
+        dev = right2d.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        if d_pooled is None:
+            d_pooled = torch.zeros((G, Dr, Cn), **f32)
+        d_pooled = d_pooled.contiguous()
+        if d_att is not None:
+            d_att = d_att.contiguous()
+        de = torch.empty((G * P, Cn), **f32)
+        du = torch.empty((G * P, H), **f32)
+        du_sum = torch.empty((G, H), **f32)
+        dright = torch.empty((G * P, Dr), **f32)
+        _lib.check(lib.get_att_pool_bwd_f32(t.data_ptr(), right2d.data_ptr(), _ld(right2d), W2.data_ptr(),
+                                            att.data_ptr(), d_pooled.data_ptr(), Dr * Cn, _ptr(d_att),
+                                            G, P, H, Dr, Cn, de.data_ptr(), du.data_ptr(), du_sum.data_ptr(),
+                                            dright.data_ptr(), Dr, 0, _stream()), "get_att_pool_bwd_f32")
+        need = ctx.needs_input_grad
+        dleft = dW1 = dW2 = None
+        W1R = W1[:, X:]
+        if need[1]:
+            gemm([(du, W1R.t())], dright, accumulate=True)
+        if need[4]:
+            dW2 = torch.empty((Cn, H), **f32)
+            gemm([(de.t(), t.t())], dW2)
+        if need[3]:
+            dW1 = torch.empty((H, X + Dr), **f32)
+            gemm([(du.t(), right2d.t())], dW1[:, X:])
+            if left is not None:
+                gemm([(du_sum.t(), left.contiguous().t())], dW1[:, :X])
+        if left is not None and need[0]:
+            dleft = torch.empty((G, X), **f32)
+            gemm([(du_sum, W1[:, :X].t())], dleft)
+        return dleft, (dright.view(G, P, Dr) if need[1] else None), None, dW1, dW2
+
+
+def concat_att(left, right, mask, W1, W2):
+    mask_u8 = (mask != 0).to(torch.uint8)
+    return ConcatAttFn.apply(left, right, mask_u8, W1, W2)
+
+
+# =================================================================================================
+# glue ops with custom kernels: linear, segment expand / pad, masked mean, cross entropy
+# =================================================================================================
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b (reference nn.Linear of the output MLP, graph_based_semantic_structure.py:69-74,121)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        y = torch.empty((x2.shape[0], W.shape[0]), dtype=torch.float32, device=x.device)
+        gemm([(x2, W.contiguous())], y, bias0=b)
+        ctx.save_for_backward(x2, W)
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x2)
+            gemm([(dy2, W.t())], dx)
+            dx = dx.view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            gemm([(dy2.t(), x2.t())], dW)
+        if ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dW, db
+
+
+def linear(x, W, b=None):
+    return LinearFn.apply(x, W, b)
+
+
+class SegmentExpandFn(torch.autograd.Function):
+    """`_pad_left_tensor` (reference basic_fc_model.py:80-92): out[r] = src[seg_of_row[r]]."""
+
+    @staticmethod
+    def forward(ctx, src, seg_of_row, offsets):
+        lib = _lib.load()
+        src = src.contiguous()
+        R, W = seg_of_row.shape[0], src.shape[1]
+        out = torch.empty((R, W), dtype=torch.float32, device=src.device)
+        _lib.check(lib.get_rows_gather_f32(src.data_ptr(), W, seg_of_row.data_ptr(), R, W, out.data_ptr(), W,
+                                           _stream()), "get_rows_gather_f32")
+        ctx.save_for_backward(offsets)
+        ctx.S = src.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        (offsets,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        W = dout.shape[1]
+        dsrc = torch.empty((ctx.S, W), dtype=torch.float32, device=dout.device)
+        _lib.check(lib.get_segment_sum_f32(dout.data_ptr(), W, offsets.data_ptr(), ctx.S, W, dsrc.data_ptr(), W,
+                                           _stream()), "get_segment_sum_f32")
+        return dsrc, None, None
+
+
+class SegmentPadFn(torch.autograd.Function):
+    """`_pad_right_tensor` (reference basic_fc_model.py:94-121) fused with the article-source concat
+    (graph_based_semantic_structure.py:157-171): out (S_slots, W+E) zero buffer, out[slot_of_row[r], :W] = src[r],
+    out[:, W:] = extra."""
+
+    @staticmethod
+    def forward(ctx, src, slot_of_row, n_slots, extra):
+        lib = _lib.load()
+        src = src.contiguous()
+        R, W = src.shape
+        E = 0 if extra is None else extra.shape[1]
+        out = torch.zeros((n_slots, W + E), dtype=torch.float32, device=src.device)
+        _lib.check(lib.get_rows_scatter_f32(src.data_ptr(), W, slot_of_row.data_ptr(), R, W, out.data_ptr(),
+                                            W + E, _stream()), "get_rows_scatter_f32")
+        if extra is not None:
+            out[:, W:].copy_(extra)
+        ctx.save_for_backward(slot_of_row)
+        ctx.W, ctx.E = W, E
+        return out
+
+    @staticmethod
+    def backward(ctx, dbuf):
+        lib = _lib.load()
+        (slot_of_row,) = ctx.saved_tensors
+        R, W = slot_of_row.shape[0], ctx.W
+        dbuf = dbuf.contiguous()
+        dsrc = None
+        if ctx.needs_input_grad[0]:
+            dsrc = torch.empty((R, W), dtype=torch.float32, device=dbuf.device)
+            _lib.check(lib.get_rows_gather_f32(dbuf.data_ptr(), W + ctx.E, slot_of_row.data_ptr(), R, W,
+                                               dsrc.data_ptr(), W, _stream()), "get_rows_gather_f32")
+        dextra = dbuf[:, W:] if (ctx.E and ctx.needs_input_grad[3]) else None
+        return dsrc, None, None, dextra
+
+
+class MaskedMeanFn(torch.autograd.Function):
+    """Claim read-out (reference graph_based_semantic_structure.py:145-153)."""
+
+    @staticmethod
+    def forward(ctx, h, ids, lens):
+        lib = _lib.load()
+        G, N, H = h.shape
+        h = h.contiguous()
+        ids = ids.to(torch.int64).contiguous()
+        lens = lens.to(torch.int64).contiguous()
+        out = torch.empty((G, H), dtype=torch.float32, device=h.device)
+        _lib.check(lib.get_masked_mean_fwd_f32(h.data_ptr(), ids.data_ptr(), lens.data_ptr(), G, N, H,
+                                               out.data_ptr(), _stream()), "get_masked_mean_fwd_f32")
+        ctx.save_for_backward(ids, lens)
+        ctx.dims = (G, N, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        ids, lens = ctx.saved_tensors
+        G, N, H = ctx.dims
+        dout = dout.contiguous()
+        dh = torch.empty((G, N, H), dtype=torch.float32, device=dout.device)
+        _lib.check(lib.get_masked_mean_bwd_f32(dout.data_ptr(), ids.data_ptr(), lens.data_ptr(), G, N, H,
+                                               dh.data_ptr(), _stream()), "get_masked_mean_bwd_f32")
+        return dh, None, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """`losses.cross_entroy` (reference losses.py:29-32): mean CE over the claims."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lib = _lib.load()
+        logits = logits.contiguous()
+        labels = labels.to(torch.int64).contiguous()
+        B, Cn = logits.shape
+        loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        _lib.check(lib.get_cross_entropy_f32(logits.data_ptr(), labels.data_ptr(), B, Cn, loss.data_ptr(),
+                                             dlogits.data_ptr(), _stream()), "get_cross_entropy_f32")
+        ctx.save_for_backward(dlogits)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * dloss, None
+
+
+def cross_entropy(logits, labels):
+    return CrossEntropyFn.apply(logits, labels)
