@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the GET hot path (BASELINE.json metric: claim-evidence pairs/s, forward+backward).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm's CPU path (oracle port)
+
+A "step" = one training pass over one mini-batch of the Snopes configuration (BASELINE.json configs[1]:
+B=32 claims, L=30, R=100, D=H=300, heads 5/2, window 3, gsl_rate 0.6, fp32): forward, cross-entropy, backward,
+gradient all-reduce (N>1) and the Adam update of the reference fitter (lr 1e-4, weight_decay 1e-3,
+Fitting/FittingFC/declare_fitter.py:57-61). Per-GPU work is fixed (weak scaling): every rank processes its own
+stream of 32-claim batches. Inputs rotate over NBATCH distinct pre-generated batches.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NBATCH = 16
+WORKLOAD = "snopes"
+METRIC = "claim_evidence_pairs_per_sec_fwd_bwd"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batches(w, n, base_seed):
+    from get_b200 import synthetic
+    return [synthetic.make_batch(w, seed=base_seed + 1000 * i) for i in range(n)]
+
+
+def graph_kernel_bytes(w, pairs):
+    """ALGORITHMIC bytes of the fused GSL kernel per launch: read F1 + adjacency, write the
+    refined aggregation: 4*R*(2H+R) per pair."""
+    return pairs * 4 * w.len_right * (2 * w.hidden + w.len_right)
+
+
+# =================================================================================================
+def run_reference(args):
+    """The reference algorithm on the host cores (oracle port; PyTorch CPU ops, all threads)."""
+    import torch
+    from get_b200 import synthetic
+    from oracle import get_oracle as O       # bench.py's reference / cpu_baseline legs may execute the oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = synthetic.get_workload(WORKLOAD)
+    res = cpu_baseline(w, steps=args.steps, warmup=args.warmup, cores=cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(w, extra={"device": "cpu"}),
+        "cpu_baseline": {"value": res["value"], "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(w, steps, warmup, cores, max_seconds=40.0):
+    """Oracle (CPU restatement of the reference modules) forward + backward on the same Snopes batches."""
+    import torch
+    from get_b200 import synthetic
+    from get_b200.model import Graph_basedSemantiStructure
+    from oracle import get_oracle as O
+    torch.set_num_threads(cores)
+    torch.manual_seed(123756)
+    model = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=False))   # parameter container only (CPU)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cfg = dict(gsl_rate=w.gsl_rate, use_claim_source=w.use_claim_source, use_article_source=w.use_article_source)
+    batches = make_batches(w, min(NBATCH, max(1, steps)), 123756)
+    tens = [synthetic.batch_to_torch(b) for b in batches]
+    pairs, t_total, done = 0, 0.0, 0
+    for i in range(warmup + steps):
+        q, d, l, kw = tens[i % len(tens)]
+        t0 = time.perf_counter()
+        O.loss_and_grads(sd, cfg, q, d, l, kw)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            t_total += dt
+            pairs += batches[i % len(tens)]["pairs"]
+            done += 1
+            if t_total > max_seconds:
+                break
+    return {"value": pairs / t_total, "ms_per_step": 1e3 * t_total / done,
+            "sample": "%d fwd+bwd steps of the same %s batches (B=%d, eval-mode dropout), %.1f s of CPU work"
+                      % (done, w.name, w.batch_claims, t_total)}
+
+
+def config_dict(w, extra=None):
+    cfg = {"workload": "%s B=%d L=%d R=%d D=%d H=%d heads=%d/%d window=%d gsl_rate=%.1f" % (
+        w.name, w.batch_claims, w.len_left, w.len_right, w.emb_dim, w.hidden, w.heads_words, w.heads_evds, w.window,
+        w.gsl_rate),
+        "step": "forward + cross-entropy + backward + grad all-reduce (N>1) + Adam(lr=1e-4, wd=1e-3)",
+        "claims_per_gpu_per_step": w.batch_claims,
+        "l2": "inputs rotate over %d distinct batches; every step also writes ~0.8 GB of activations (> 126 MB L2)" % NBATCH}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from get_b200 import _lib, ops, synthetic
+    from get_b200.ddp import FlatGradAllReduce, trainable_named_parameters
+    from get_b200.keywords import KeyWordSettings as K
+    from get_b200.model import Graph_basedSemantiStructure
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = synthetic.get_workload(WORKLOAD)
+    torch.manual_seed(123756)
+    model = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=True)).to(dev)
+    model.train()
+    named = trainable_named_parameters(model)
+    params = [p for _, p in named]
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-3, fused=True)
+    reducer = FlatGradAllReduce(params)
+
+    batches = make_batches(w, NBATCH, 123756 + 7919 * rank)
+    host = [synthetic.batch_to_torch(b, device="cpu", pin=True) for b in batches]
+    resident = [synthetic.batch_to_torch(b, device=dev) for b in batches]
+
+    def to_device(hb):
+        q, d, l, kw = hb
+        mv = lambda t: t.to(dev, non_blocking=True) if torch.is_tensor(t) else t
+        kw2 = {k: (tuple(mv(x) for x in v) if isinstance(v, tuple) else mv(v)) for k, v in kw.items()}
+        return mv(q), mv(d), mv(l), kw2
+
+    def h2d_bytes(hb):
+        q, d, l, kw = hb
+        n = q.numel() * q.element_size() + d.numel() * d.element_size() + l.numel() * l.element_size()
+        for v in kw.values():
+            for x in (v if isinstance(v, tuple) else (v,)):
+                if torch.is_tensor(x):
+                    n += x.numel() * x.element_size()
+        return n
+
+    def step(db):
+        q, d, l, kw = db
+        opt.zero_grad(set_to_none=True)
+        logits = model(q, d, **kw)
+        loss = ops.cross_entropy(logits, l)
+        loss.backward()
+        reducer.reduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------
+    for i in range(max(3, args.warmup)):
+        step(resident[i % NBATCH])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM --------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ops.PROFILE_GSL_EVENTS = []
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pairs = 0
+    for i in range(args.steps):
+        b = (i + args.warmup) % NBATCH
+        step(resident[b])
+        pairs += batches[b]["pairs"]
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = e0.elapsed_time(e1) / 1e3
+    gsl_events = ops.PROFILE_GSL_EVENTS
+    ops.PROFILE_GSL_EVENTS = None
+    gsl_ms = [a.elapsed_time(b) for a, b, _ in gsl_events]
+    gsl_pairs = [n for _, _, n in gsl_events]
+
+    # ---- timed region 2: end to end from pinned host memory --------------------------------------
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2.record()
+    pairs_e2e, h2d, d2h = 0, 0, 0
+    for i in range(args.steps):
+        b = (i + args.warmup) % NBATCH
+        loss = step(to_device(host[b]))
+        _ = float(loss.item())                      # device -> host read of the step's result
+        pairs_e2e += batches[b]["pairs"]
+        h2d += h2d_bytes(host[b])
+        d2h += 4
+    e3.record()
+    barrier()
+    t_e2e = max(time.perf_counter() - t0, e2.elapsed_time(e3) / 1e3)
+
+    # ---- reduce over ranks: max time, summed pairs ------------------------------------------------
+    stats = torch.tensor([t_dev, t_e2e, float(pairs), float(pairs_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = stats.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = stats.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e = float(tmax[0]), float(tmax[1])
+        pairs, pairs_e2e = float(tsum[2]), float(tsum[3])
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        gsl_avg_ms = float(np.mean(gsl_ms)) if gsl_ms else None
+        gsl_bytes = float(np.mean([graph_kernel_bytes(w, n) for n in gsl_pairs])) if gsl_pairs else None
+        achieved = gsl_bytes / (gsl_avg_ms * 1e-3) / 1e9 if gsl_ms else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gsl_fused_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        cpu = None
+        if world == 1 or True:
+            cores = os.cpu_count() or 1
+            cpu = cpu_baseline(w, steps=5, warmup=1, cores=cores, max_seconds=25.0)
+        line = {
+            "metric": METRIC, "value": pairs / t_dev, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(w, {"parallelism": "dp%d" % world, "mean_pairs_per_step_per_gpu": pairs / args.steps / world,
+                                      "grad_allreduce_bytes": reducer.nbytes if world > 1 else 0,
+                                      "wall_s_timed_region": t_wall}),
+            "clocks": clocks,
+            "e2e": {"value": pairs_e2e / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
+                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "graph_kernel<FUSED> (get_gsl_fused_f32)", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "avg_launch_ms": gsl_avg_ms, "algorithmic_bytes_per_launch": gsl_bytes,
+                         "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
+            "cpu_baseline": {"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 12:
+            args.steps = 12          # bounded sample: ~1 s of CPU work per step
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,9 @@ from ._lib import (EPI_DGATE_R, EPI_DROPOUT_OUT, EPI_SIGMOID, EPI_STORE, EPI_TAN
                    EPI_TANH_ROWGROUP, GemmDesc)
 
 _SM_COUNT = 148
+# bench.py sets this to a list to time the fused GSL kernel with CUDA events on its launch stream:
+# entries are (start_event, stop_event, n_graphs)
+PROFILE_GSL_EVENTS = None
 
 
 def _stream() -> int:
@@ -143,9 +146,16 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     score = torch.empty((G, N), dtype=torch.float32, device=feat.device) if want_score else None
     keep = torch.empty((G, N), dtype=torch.uint8, device=feat.device)
     out = torch.empty_like(feat)
+    prof = PROFILE_GSL_EVENTS
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(lib.get_gsl_fused_f32(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, int(k),
                                      float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF,
                                      _ptr(score), keep.data_ptr(), out.data_ptr(), _stream()), "get_gsl_fused_f32")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, G))
     return score, keep, out
 
 

@@ -218,4 +218,7 @@ def near_tie_graphs(score: Tensor, rate: float, tol: float = 1e-5) -> Tensor:
     top, _ = s.topk(min(k + 1, s.shape[1]), 1)
     if k >= s.shape[1]:
         return torch.zeros(s.shape[0], dtype=torch.bool)
-    return (top[:, k - 1] - top[:, k]).abs() < tol
+    gap = (top[:, k - 1] - top[:, k]).abs()
+    # gap == 0 is an exact tie, which only happens among pad nodes (identical features, zero adjacency rows
+    # and columns): whichever of them is kept, the refined adjacency is the same
+    return (gap < tol) & (gap > 0)
