@@ -31,6 +31,8 @@ class GemmDesc(C.Structure):
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_cols", C.c_int32), ("_pad0", C.c_int32),
         ("drop_out_p", C.c_float), ("drop_out_seed", C.c_uint32),
         ("split_k", C.c_int32), ("_pad1", C.c_int32), ("workspace", C.c_void_p),
+        ("B_hi", C.c_void_p * GEMM_MAX_SEG), ("B_lo", C.c_void_p * GEMM_MAX_SEG),
+        ("ld_split", C.c_int64 * GEMM_MAX_SEG), ("tc_mode", C.c_int32), ("tc_n_tiles", C.c_int32),
     ]
 
 
@@ -39,6 +41,8 @@ _P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 SIGNATURES = {
     "get_gemm_f32": (_I, [C.POINTER(GemmDesc), _P]),
     "get_gemm_f32_launches": (_I, [C.POINTER(GemmDesc)]),
+    "get_gemm_f32_uses_tc": (_I, [C.POINTER(GemmDesc)]),
+    "get_split_tf32_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _L, _P]),
     "get_graph_aggregate_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "get_gsl_fused_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P]),
     "get_gsl_mask_adj_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

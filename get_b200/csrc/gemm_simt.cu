@@ -7,7 +7,8 @@
 // shared memory with register prefetch, 128-bit global loads whenever the operand allows it. Row gather
 // (embedding lookup, gbss.py:100) and dropout (wrapper.py:189-190) are applied while the A tile is loaded.
 // Split-K writes per-split partial tiles and a second kernel reduces them in a fixed order (deterministic).
-#include "common.cuh"
+#include "gemm_common.cuh"
+#include <string.h>
 
 namespace getb {
 
@@ -15,150 +16,6 @@ constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
 constexpr int NTHREADS = (BM / TM) * (BN / TN);  // 256
 constexpr int PAD = 4;
 static_assert(NTHREADS == 256, "tile config");
-
-struct GemmOp {
-  const float* ptr;
-  int64_t ld;
-  const int64_t* rowidx;
-  int trans;
-  int vec;
-};
-
-struct GemmParams {
-  GemmOp A[GET_GEMM_MAX_SEG];
-  GemmOp B[GET_GEMM_MAX_SEG];
-  int K[GET_GEMM_MAX_SEG];
-  int nseg, M, N;
-  float* C;
-  int64_t ldc;
-  float alpha;
-  int accumulate, epilogue;
-  const float *bias0, *bias1, *aux0, *aux1;
-  int64_t ld_aux0, ld_aux1;
-  float* out1;
-  int64_t ld_out1;
-  int group_rows;
-  uint32_t drop_thr, drop_seed;
-  int drop_cols;
-  float drop_scale;
-  uint32_t drop_out_thr, drop_out_seed;
-  float drop_out_scale;
-  int split_k, tiles_per_split, tiles_total;
-  float* workspace;
-  int vec_epi;
-  int ntn;  // number of tiles along N
-};
-
-// ---- epilogue on up to 4 consecutive columns (n .. n+3) of row m ------------------------------
-__device__ __forceinline__ void load4(const float* base, bool vec, int nvalid, float v[4]) {
-  if (vec) {
-    float4 t = *reinterpret_cast<const float4*>(base);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = e < nvalid ? base[e] : 0.f;
-  }
-}
-__device__ __forceinline__ void store4(float* base, bool vec, int nvalid, const float v[4]) {
-  if (vec) {
-    *reinterpret_cast<float4*>(base) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (e < nvalid) base[e] = v[e];
-  }
-}
-
-__device__ __forceinline__ void epilogue4(const GemmParams& p, int m, int n, float acc[4]) {
-  const int nvalid = min(4, p.N - n);
-  const bool vec = p.vec_epi != 0;  // host guarantees N % 4 == 0 and 16-byte alignment of every pointer used
-  float v[4], b[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = p.alpha * acc[e];
-  if (p.bias0) {
-    load4(p.bias0 + n, vec, nvalid, b);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] += b[e];
-  }
-  if (p.bias1) {
-    load4(p.bias1 + n, vec, nvalid, b);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] += b[e];
-  }
-  float* crow = p.C + (int64_t)m * p.ldc + n;
-  float a0[4], a1[4], o[4];
-  switch (p.epilogue) {
-    case GET_EPI_STORE: {
-      if (p.accumulate) {
-        load4(crow, vec, nvalid, o);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] += o[e];
-      }
-      store4(crow, vec, nvalid, v);
-    } break;
-    case GET_EPI_SIGMOID: {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = sigmoidf_(v[e]);
-      store4(crow, vec, nvalid, v);
-      if (p.out1) {
-        load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, a0);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = v[e] * a0[e];
-        store4(p.out1 + (int64_t)m * p.ld_out1 + n, vec, nvalid, o);
-      }
-    } break;
-    case GET_EPI_TANH_BLEND: {
-      load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, a0);  // z
-      load4(p.aux1 + (int64_t)m * p.ld_aux1 + n, vec, nvalid, a1);  // x
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        v[e] = tanhf(v[e]);
-        o[e] = v[e] * a0[e] + a1[e] * (1.0f - a0[e]);
-      }
-      if (p.out1) store4(p.out1 + (int64_t)m * p.ld_out1 + n, vec, nvalid, v);
-      store4(crow, vec, nvalid, o);
-    } break;
-    case GET_EPI_TANH_ROWGROUP: {
-      load4(p.aux0 + (int64_t)(m / p.group_rows) * p.ld_aux0 + n, vec, nvalid, a0);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = tanhf(v[e] + a0[e]);
-      store4(crow, vec, nvalid, v);
-    } break;
-    case GET_EPI_DGATE_R: {
-      load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, a0);  // x
-      load4(p.aux1 + (int64_t)m * p.ld_aux1 + n, vec, nvalid, a1);  // r
-      float* o1 = p.out1 + (int64_t)m * p.ld_out1 + n;
-      load4(o1, vec, nvalid, o);
-      float c[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        c[e] = v[e] * a0[e] * a1[e] * (1.0f - a1[e]);
-        o[e] += v[e] * a1[e];
-      }
-      store4(crow, vec, nvalid, c);
-      store4(o1, vec, nvalid, o);
-    } break;
-    case GET_EPI_DROPOUT_OUT: {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        bool keep = drop_keep(p.drop_out_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + e), p.drop_out_thr);
-        v[e] = keep ? v[e] * p.drop_out_scale : 0.f;
-      }
-      if (p.accumulate) {
-        load4(crow, vec, nvalid, o);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] += o[e];
-      }
-      store4(crow, vec, nvalid, v);
-    } break;
-    case GET_EPI_TANH: {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = tanhf(v[e]);
-      store4(crow, vec, nvalid, v);
-    } break;
-    default: break;
-  }
-}
 
 // ---- tile loaders -------------------------------------------------------------------------------
 // A tile of ROWS x BK elements is fetched as NV "quads" per thread. Quad f = tid + j*NTHREADS:
@@ -363,7 +220,7 @@ static bool op_vec_ok(const get_gemm_operand& o, int rows, int k) {
   return o.trans == 0 ? (k % 4) == 0 : (rows % 4) == 0;
 }
 
-static int build_params(const get_gemm_desc* d, GemmParams& p) {
+int gemm_build_params(const get_gemm_desc* d, GemmParams& p) {
   GETB_REQUIRE(d != nullptr, "get_gemm_f32: null descriptor");
   GETB_REQUIRE(d->nseg >= 1 && d->nseg <= GET_GEMM_MAX_SEG, "get_gemm_f32: nseg=%d out of range", d->nseg);
   GETB_REQUIRE(d->M >= 0 && d->N >= 0, "get_gemm_f32: negative M/N");
@@ -429,17 +286,22 @@ using namespace getb;
 
 extern "C" int get_gemm_f32_launches(const get_gemm_desc* d) {
   GemmParams p;
-  if (build_params(d, p) != 0) return -1;
+  if (gemm_build_params(d, p) != 0) return -1;
   if (p.M == 0 || p.N == 0) return 0;
   return p.split_k > 1 ? 2 : 1;
 }
 
 extern "C" int get_gemm_f32(const get_gemm_desc* d, void* stream) {
   GemmParams p;
-  int rc = build_params(d, p);
+  int rc = gemm_build_params(d, p);
   if (rc != 0) return rc;
   if (p.M == 0 || p.N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->tc_mode == 1) {
+    const int trc = gemm_tc_launch(d, p, st);
+    if (trc == 0) return 0;
+    if (trc < 0) return trc;   // launch error; trc == 1: not eligible -> exact SIMT path below
+  }
   const int64_t ntm = (p.M + BM - 1) / BM;
   const int64_t nblk = ntm * p.ntn;
   GETB_REQUIRE(nblk < (int64_t)2147483647, "get_gemm_f32: too many tiles");

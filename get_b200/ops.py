@@ -6,6 +6,7 @@ hot path is a kernel of libget_b200.so. Nothing in this file falls back to torch
 GPU is missing -- the calls raise.
 """
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -66,6 +67,36 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
+# Tensor-core (tcgen05, 3xTF32) path for the weight GEMMs; GET_B200_TC=0 forces the exact SIMT path everywhere.
+TC_ENABLED = os.environ.get("GET_B200_TC", "1") != "0"
+DEBUG_TC_REPORT = False      # tests: record in LAST_GEMM_USED_TC whether the last gemm() ran on the tcgen05 path
+LAST_GEMM_USED_TC = None
+_split_cache = {}
+
+
+def split_weight(b: torch.Tensor):
+    """(hi, lo) k-contiguous TF32 split of a weight view b (logical (N, K), any strides), cached per
+    (storage address, shape, strides) and refreshed when the parameter's version counter moves (optimizer step)."""
+    key = (b.data_ptr(), tuple(b.shape), tuple(b.stride()))
+    ent = _split_cache.get(key)
+    ver = b._version
+    if ent is not None and ent[0] == ver:
+        return ent[1], ent[2]
+    lib = _lib.load()
+    _chk_f32(b, "B")
+    N, K = b.shape
+    ldo = (K + 3) // 4 * 4
+    if ent is not None:
+        hi, lo = ent[1], ent[2]
+    else:
+        hi = torch.zeros((N, ldo), dtype=torch.float32, device=b.device)
+        lo = torch.zeros((N, ldo), dtype=torch.float32, device=b.device)
+    _lib.check(lib.get_split_tf32_f32(b.data_ptr(), b.stride(0), b.stride(1), N, K, hi.data_ptr(), lo.data_ptr(), ldo,
+                                      _stream()), "get_split_tf32_f32")
+    _split_cache[key] = (ver, hi, lo)
+    return hi, lo
+
+
 def new_seed() -> int:
     """32-bit dropout seed drawn from torch's CPU generator (follows torch.manual_seed)."""
     return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
@@ -74,8 +105,10 @@ def new_seed() -> int:
 def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tensor, *, epilogue: int = EPI_STORE,
          bias0=None, bias1=None, aux0=None, aux1=None, out1=None, group_rows: int = 0, alpha: float = 1.0,
          accumulate: bool = False, rowidx: Optional[torch.Tensor] = None, drop_p: float = 0.0, drop_seed: int = 0,
-         drop_cols: int = 0, drop_out_p: float = 0.0, drop_out_seed: int = 0, split_k: Optional[int] = None):
-    """out[m,n] = epilogue(sum_s A_s[m,:] . B_s[n,:]); A_s logical (M,K_s), B_s logical (N,K_s)."""
+         drop_cols: int = 0, drop_out_p: float = 0.0, drop_out_seed: int = 0, split_k: Optional[int] = None,
+         tc: bool = False, tc_n_tiles: int = 0):
+    """out[m,n] = epilogue(sum_s A_s[m,:] . B_s[n,:]); A_s logical (M,K_s), B_s logical (N,K_s).
+    tc=True (every B_s is a weight): offer the pre-split weights so the library may take the tcgen05 path."""
     lib = _lib.load()
     M, N = out.shape
     d = GemmDesc()
@@ -117,6 +150,16 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
         ws = torch.empty((split_k * M * N,), dtype=torch.float32, device=out.device)
         d.workspace = ws.data_ptr()
     d.split_k = split_k
+    if tc and TC_ENABLED and split_k <= 1 and M >= 64:
+        keep_alive = []
+        for s, (a, b) in enumerate(segments):
+            hi, lo = split_weight(b)
+            keep_alive.append((hi, lo))
+            d.B_hi[s], d.B_lo[s], d.ld_split[s] = hi.data_ptr(), lo.data_ptr(), hi.stride(0)
+        d.tc_mode, d.tc_n_tiles = 1, tc_n_tiles
+    if DEBUG_TC_REPORT:
+        global LAST_GEMM_USED_TC
+        LAST_GEMM_USED_TC = int(lib.get_gemm_f32_uses_tc(C.byref(d)))
     _lib.check(lib.get_gemm_f32(C.byref(d), _stream()), "get_gemm_f32")
     return out
 
@@ -220,17 +263,17 @@ class GGNNLayerFn(torch.autograd.Function):
         drop = dict(drop_p=p_drop, drop_seed=seed, drop_cols=Din) if p_drop > 0 else {}
         if feat is not None:
             feat2d = _rows2d(feat)
-            gemm([(feat2d, Wp)], x, **drop)
+            gemm([(feat2d, Wp)], x, tc=True, **drop)
             rowidx = None
         else:
             rowidx = ids.reshape(-1).to(torch.int64).contiguous()
             # logical A = table rows gathered by rowidx; shape bookkeeping through an expanded view
             _chk_f32(table, "table")
             a_view = Raw(table.data_ptr(), table.stride(0), 0, (M, Din))
-            gemm([(a_view, Wp)], x, rowidx=rowidx, **drop)
+            gemm([(a_view, Wp)], x, rowidx=rowidx, tc=True, **drop)
         a = torch.empty((M, H), **f32)
         if pre_agg is not None:
-            gemm([(_rows2d(pre_agg), Wp)], a)
+            gemm([(_rows2d(pre_agg), Wp)], a, tc=True)
         else:
             graph_aggregate(adj, x.view(G, N, H), keep, out=a.view(G, N, H))
         z = torch.empty((M, H), **f32)
@@ -238,9 +281,10 @@ class GGNNLayerFn(torch.autograd.Function):
         rx = torch.empty((M, H), **f32)
         h = torch.empty((M, H), **f32)
         out = torch.empty((M, H), **f32)
-        gemm([(a, Wz0), (x, Wz1)], z, epilogue=EPI_SIGMOID, bias0=bz0, bias1=bz1)
-        gemm([(a, Wr0), (x, Wr1)], r, epilogue=EPI_SIGMOID, bias0=br0, bias1=br1, aux0=x, out1=rx)
-        gemm([(a, Wh0), (rx, Wh1)], out, epilogue=EPI_TANH_BLEND, bias0=bh0, bias1=bh1, aux0=z, aux1=x, out1=h)
+        gemm([(a, Wz0), (x, Wz1)], z, epilogue=EPI_SIGMOID, bias0=bz0, bias1=bz1, tc=True)
+        gemm([(a, Wr0), (x, Wr1)], r, epilogue=EPI_SIGMOID, bias0=br0, bias1=br1, aux0=x, out1=rx, tc=True)
+        gemm([(a, Wh0), (rx, Wh1)], out, epilogue=EPI_TANH_BLEND, bias0=bh0, bias1=bh1, aux0=z, aux1=x, out1=h,
+             tc=True)
         ctx.save_for_backward(adj, feat, table, rowidx, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1)
         ctx.p_drop, ctx.seed, ctx.dims = p_drop, seed, (G, N, H, Din)
         return out.view(G, N, H)
@@ -263,11 +307,11 @@ class GGNNLayerFn(torch.autograd.Function):
                                              dhp.data_ptr(), dzp.data_ptr(), dx.data_ptr(), _stream()),
                    "get_ggnn_gate_bwd_f32")
         # d(rx) = dhp @ Wh1 ; drp = d(rx)*x*r*(1-r) ; dx += d(rx)*r
-        gemm([(dhp, Wh1.t())], drp, epilogue=EPI_DGATE_R, aux0=x, aux1=r, out1=dx)
+        gemm([(dhp, Wh1.t())], drp, epilogue=EPI_DGATE_R, aux0=x, aux1=r, out1=dx, tc=True)
         # da = dhp@Wh0 + dzp@Wz0 + drp@Wr0
-        gemm([(dhp, Wh0.t()), (dzp, Wz0.t()), (drp, Wr0.t())], da)
+        gemm([(dhp, Wh0.t()), (dzp, Wz0.t()), (drp, Wr0.t())], da, tc=True)
         # dx += dzp@Wz1 + drp@Wr1 + adj'^T @ da
-        gemm([(dzp, Wz1.t()), (drp, Wr1.t())], dx, accumulate=True)
+        gemm([(dzp, Wz1.t()), (drp, Wr1.t())], dx, accumulate=True, tc=True)
         graph_aggregate(adj, da.view(G, N, H), keep, out=dx.view(G, N, H), transpose=True, accumulate=True)
         need = ctx.needs_input_grad
         grads = [None] * 21
@@ -309,9 +353,10 @@ class GGNNLayerFn(torch.autograd.Function):
         if feat is not None and need[1]:
             dfeat = torch.empty((M, Din), **f32)
             if ctx.p_drop > 0:
-                gemm([(dx, Wp.t())], dfeat, epilogue=EPI_DROPOUT_OUT, drop_out_p=ctx.p_drop, drop_out_seed=ctx.seed)
+                gemm([(dx, Wp.t())], dfeat, epilogue=EPI_DROPOUT_OUT, drop_out_p=ctx.p_drop, drop_out_seed=ctx.seed,
+                     tc=True)
             else:
-                gemm([(dx, Wp.t())], dfeat)
+                gemm([(dx, Wp.t())], dfeat, tc=True)
             grads[1] = dfeat.view(G, N, Din)
         return tuple(grads)
 
@@ -340,10 +385,10 @@ class ConcatAttFn(torch.autograd.Function):
         t = torch.empty((G * P, H), **f32)
         if left is not None:
             lp = torch.empty((G, H), **f32)
-            gemm([(left.contiguous(), W1[:, :X])], lp)
-            gemm([(right2d, W1[:, X:])], t, epilogue=EPI_TANH_ROWGROUP, aux0=lp, group_rows=P)
+            gemm([(left.contiguous(), W1[:, :X])], lp, tc=True)
+            gemm([(right2d, W1[:, X:])], t, epilogue=EPI_TANH_ROWGROUP, aux0=lp, group_rows=P, tc=True)
         else:
-            gemm([(right2d, W1)], t, epilogue=EPI_TANH)
+            gemm([(right2d, W1)], t, epilogue=EPI_TANH, tc=True)
         att = torch.empty((G, P, Cn), **f32)
         pooled = torch.empty((G, Dr, Cn), **f32)
         mask_u8 = mask_u8.contiguous()
@@ -378,7 +423,7 @@ class ConcatAttFn(torch.autograd.Function):
         dleft = dW1 = dW2 = None
         W1R = W1[:, X:]
         if need[1]:
-            gemm([(du, W1R.t())], dright, accumulate=True)
+            gemm([(du, W1R.t())], dright, accumulate=True, tc=True)
         if need[4]:
             dW2 = torch.empty((Cn, H), **f32)
             gemm([(de.t(), t.t())], dW2)
@@ -389,7 +434,7 @@ class ConcatAttFn(torch.autograd.Function):
                 gemm([(du_sum.t(), left.contiguous().t())], dW1[:, :X])
         if left is not None and need[0]:
             dleft = torch.empty((G, X), **f32)
-            gemm([(du_sum, W1[:, :X].t())], dleft)
+            gemm([(du_sum, W1[:, :X].t())], dleft, tc=True)
         return dleft, (dright.view(G, P, Dr) if need[1] else None), None, dW1, dW2
 
 

@@ -90,9 +90,29 @@ typedef struct get_gemm_desc {
    * order by a second kernel (deterministic), then the epilogue is applied. */
   int32_t split_k; int32_t _pad1;
   float* workspace;
+  /* Tensor-core path (tcgen05, 3xTF32 error-compensated: fp32-level accuracy). Used when tc_mode == 1 and the
+   * descriptor is eligible: every A segment contiguous along k (trans == 0, ld % 4 == 0, K % 4 == 0, K >= 32),
+   * no split-K, and every B segment ALSO given pre-split as two k-contiguous (N, K[s]) row-major matrices
+   * B_hi[s] (tf32-rounded) and B_lo[s] (= B - B_hi) with leading dimension ld_split[s] (see
+   * get_split_tf32_f32; a transposed B is simply split into a k-contiguous copy). B[s] stays the original
+   * operand: ineligible descriptors fall back to the exact SIMT path. tc_n_tiles: CTA tiles along N (0 = auto). */
+  const float* B_hi[GET_GEMM_MAX_SEG];
+  const float* B_lo[GET_GEMM_MAX_SEG];
+  int64_t ld_split[GET_GEMM_MAX_SEG];
+  int32_t tc_mode; int32_t tc_n_tiles;
 } get_gemm_desc;
 
 int get_gemm_f32(const get_gemm_desc* desc, void* stream);
+
+/* 1 if the descriptor would run on the tcgen05 path, 0 if on the SIMT path, <0 on invalid descriptors. */
+int get_gemm_f32_uses_tc(const get_gemm_desc* desc);
+
+/* Error-compensated TF32 split of a weight matrix for the tensor-core path:
+ * hi = tf32_round_nearest(src), lo = src - hi. src is a logical (rows, cols) matrix addressed as
+ * src[r*ld_r + c*ld_c] (so a transposed view can be split into a k-contiguous copy); hi/lo are (rows, cols)
+ * row-major with leading dimension ld_out. */
+int get_split_tf32_f32(const float* src, int64_t ld_r, int64_t ld_c, int rows, int cols,
+                       float* hi, float* lo, int64_t ld_out, void* stream);
 
 /* Number of kernels get_gemm_f32 will launch for this descriptor (1, or 2 with split-K). */
 int get_gemm_f32_launches(const get_gemm_desc* desc);

@@ -52,9 +52,10 @@ def test_gemm_descriptor_layout_matches_header():
 #include <stddef.h>
 #include "get_b200.h"
 int main(void){
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(get_gemm_desc), sizeof(get_gemm_operand),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(get_gemm_desc), sizeof(get_gemm_operand),
     offsetof(get_gemm_desc,B), offsetof(get_gemm_desc,K), offsetof(get_gemm_desc,C), offsetof(get_gemm_desc,bias0),
-    offsetof(get_gemm_desc,group_rows), offsetof(get_gemm_desc,drop_out_p), offsetof(get_gemm_desc,workspace));
+    offsetof(get_gemm_desc,group_rows), offsetof(get_gemm_desc,drop_out_p), offsetof(get_gemm_desc,workspace),
+    offsetof(get_gemm_desc,ld_split), offsetof(get_gemm_desc,tc_n_tiles));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -65,7 +66,7 @@ int main(void){
         got = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
     D = _lib.GemmDesc
     want = [ctypes.sizeof(D), ctypes.sizeof(_lib.GemmOperand), D.B.offset, D.K.offset, D.C.offset, D.bias0.offset,
-            D.group_rows.offset, D.drop_out_p.offset, D.workspace.offset]
+            D.group_rows.offset, D.drop_out_p.offset, D.workspace.offset, D.ld_split.offset, D.tc_n_tiles.offset]
     assert got == want
 
 
