@@ -407,11 +407,22 @@ int gemm_tc_launch(const get_gemm_desc* d, const GemmParams& p, cudaStream_t st)
     if (!make_b_map(&maps.lo[s], d->B_lo[s], p.N, p.K[s], d->ld_split[s], cfg.BN)) return 1;
   }
   const size_t smem = (size_t)cfg.stages * (2 * TC_A_TILE_BYTES + 2 * cfg.BN * 128) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
+  static int max_dyn = -1;   // opt-in limit (227 KB per CTA) minus this kernel's static shared memory
+  if (max_dyn < 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tc_kernel);
+    if (e == cudaSuccess) {
+      const int want = 227 * 1024 - (int)((fa.sharedSizeBytes + 1023) / 1024 * 1024);
+      e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      if (e == cudaSuccess) max_dyn = want;
+    }
+    if (e != cudaSuccess) {
+      set_error("gemm_tc_kernel: cannot opt in to large shared memory: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return -(int)e - 1000;
+    }
   }
+  if ((int)smem > max_dyn) return 1;
   dim3 grid((unsigned)((p.N + cfg.BN - 1) / cfg.BN), (unsigned)((p.M + TC_BM - 1) / TC_BM), 1);
   if (grid.y > 65535) return 1;
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, cfg, maps);

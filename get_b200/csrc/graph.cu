@@ -1,14 +1,20 @@
 // Per-graph kernels of the GET hot path (HBM-bound part).
 //
-//  * graph_kernel<FUSED=false>: out[g] (+)= op(adj'[g]) @ x[g]                       reference Models/BiDAF/wrapper.py:192
-//  * graph_kernel<FUSED=true> : node scorer (GGNN with out_features=1, wrapper.py:167) -> top-k keep set
-//                               (wrapper.py:215-219) -> refined aggregation (wrapper.py:221-225 + :192)
-//                               in ONE pass; the dense (N,N) mask of the reference is never materialised.
-//  * gsl_mask_adj_kernel      : stand-alone GSL.forward (wrapper.py:215-227) for the op-level surface.
+//  * <FUSED=false>: out[g] (+)= op(adj'[g]) @ x[g]                                   reference Models/BiDAF/wrapper.py:192
+//  * <FUSED=true> : node scorer (GGNN with out_features=1, wrapper.py:167) -> top-k keep set
+//                   (wrapper.py:215-219) -> refined aggregation (wrapper.py:221-225 + :192)
+//                   in ONE pass; the dense (N,N) mask of the reference is never materialised.
+//  * gsl_mask_adj_kernel: stand-alone GSL.forward (wrapper.py:215-227) for the op-level surface.
 //
-// One CTA per graph. The adjacency tile (N x N fp32) is staged in shared memory once (row stride padded to an
-// odd number of words so row- and column-wise scans are bank-conflict free); node-feature rows are streamed
-// with 128-bit loads, one warp per output row, skipping zero adjacency entries by warp ballot.
+// Two implementations behind the same entry points, one CTA per graph:
+//  * graph_smem_kernel (the fast path, taken whenever one graph fits a CTA's shared memory -- Snopes / PolitiFact
+//    shapes: 100 x 300 features = 120 KB + 100 x 100 adjacency = 40 KB): the adjacency and the node features are
+//    staged ONCE by TMA bulk copies (cp.async.bulk + mbarrier complete_tx; features in row chunks so the scorer
+//    starts on the first chunk while the rest is in flight); scorer dot products, SpMV, top-k, dropout and the
+//    neighbour gather-and-weighted-sum then run entirely out of shared memory with 128-bit accesses and warp
+//    shuffles; every HBM byte of the graph is read exactly once and every output row written once, coalesced.
+//  * graph_kernel (generic fallback, any N/H/alignment): adjacency in shared memory when it fits, feature rows
+//    streamed through L2 with 128-bit loads.
 #include "common.cuh"
 
 namespace getb {
@@ -223,6 +229,248 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
   }
 }
 
+// =====================================================================================================
+// Fast path: whole graph resident in shared memory, staged by TMA bulk copies.
+// =====================================================================================================
+constexpr int GS_THREADS = 512;
+constexpr int GS_WARPS = GS_THREADS / 32;
+constexpr int GS_CHUNKS = 4;            // feature rows arrive in GS_CHUNKS bulk copies, one mbarrier each
+constexpr int GS_MAX_QUADS = 4;         // H <= 32*4*4 = 512 on the fast path
+constexpr size_t GS_SMEM_LIMIT = 226 * 1024;
+
+__device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gs_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void gs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gs_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = gs_smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();   // a lost copy must fail loudly, never hang the GPU
+  }
+}
+// global -> shared bulk copy (TMA engine, no tensor map needed for a contiguous block); bytes % 16 == 0
+__device__ __forceinline__ void gs_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(gs_smem_u32(dst)), "l"(src), "r"(bytes), "r"(gs_smem_u32(bar))
+               : "memory");
+}
+
+// smem layout (floats): [F N*H] [adj N*N] [sp N] [sa N] [score N] | keep N bytes | mbarriers (8-byte aligned)
+// NQ = ceil(H/4/32): float4 "quads" of a feature row owned by each lane (compile-time so the row loops unroll exactly)
+template <bool FUSED, int NQ>
+__global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_constant__ GraphParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, H = p.H, HQ = H >> 2;
+  float* sF = smem;
+  float* sA = sF + (size_t)N * H;
+  float* s_sp = sA + (size_t)N * N;
+  float* s_sa = s_sp + N;
+  float* s_score = s_sa + N;
+  uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_score + N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_keep + ((N + 15) & ~15));   // [0] adjacency, [1..GS_CHUNKS] features
+
+  const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
+  const float* __restrict__ gx = p.x + (int64_t)g * N * H;
+  float* __restrict__ gout = p.out + (int64_t)g * N * H;
+  const int rows_per_chunk = (N + GS_CHUNKS - 1) / GS_CHUNKS;
+  const bool last_ok = (lane + (NQ - 1) * 32) < HQ;   // does this lane own a quad in the last (partial) group?
+
+  if (tid == 0) {
+    for (int b = 0; b <= GS_CHUNKS; ++b) gs_mbar_init(&bars[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int c = 0; c < GS_CHUNKS; ++c) {
+      const int r0 = c * rows_per_chunk;
+      const int r1 = min(N, r0 + rows_per_chunk);
+      if (r1 > r0) {
+        const uint32_t bytes = (uint32_t)(r1 - r0) * (uint32_t)H * 4u;
+        gs_mbar_expect_tx(&bars[1 + c], bytes);
+        gs_bulk_g2s(sF + (size_t)r0 * H, gx + (size_t)r0 * H, bytes, &bars[1 + c]);
+      } else {
+        gs_mbar_expect_tx(&bars[1 + c], 0);
+      }
+      if (c == 0) {
+        const uint32_t abytes = (uint32_t)N * (uint32_t)N * 4u;
+        gs_mbar_expect_tx(&bars[0], abytes);
+        gs_bulk_g2s(sA, gadj, abytes, &bars[0]);
+      }
+    }
+  }
+
+  if (FUSED) {
+    // ---- s_p[i] = drop_s(F[i,:]) . wp  (warp per row, chunk by chunk as the copies land) --------------
+    float4 wq[NQ];
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) {
+      const int q = lane + u * 32;
+      wq[u] = q < HQ ? __ldg(reinterpret_cast<const float4*>(p.wp) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int c = 0; c < GS_CHUNKS; ++c) {
+      gs_mbar_wait(&bars[1 + c], 0);
+      const int r1 = min(N, (c + 1) * rows_per_chunk);
+      for (int i = c * rows_per_chunk + warp; i < r1; i += GS_WARPS) {
+        const float4* row = reinterpret_cast<const float4*>(sF + (size_t)i * H);
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+          if (u < NQ - 1 || last_ok) {
+            const int q = lane + u * 32;
+            float4 f = row[q];
+            if (p.thr) {
+              const uint64_t base = ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)q * 4;
+              f.x = drop_keep(p.seed_s, base + 0, p.thr) ? f.x * p.scale : 0.f;
+              f.y = drop_keep(p.seed_s, base + 1, p.thr) ? f.y * p.scale : 0.f;
+              f.z = drop_keep(p.seed_s, base + 2, p.thr) ? f.z * p.scale : 0.f;
+              f.w = drop_keep(p.seed_s, base + 3, p.thr) ? f.w * p.scale : 0.f;
+            }
+            acc = fmaf(f.x, wq[u].x, acc); acc = fmaf(f.y, wq[u].y, acc);
+            acc = fmaf(f.z, wq[u].z, acc); acc = fmaf(f.w, wq[u].w, acc);
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_sp[i] = acc;
+      }
+    }
+    gs_mbar_wait(&bars[0], 0);
+    __syncthreads();
+    // ---- s_a = adj @ s_p (warp per row) ---------------------------------------------------------------
+    for (int i = warp; i < N; i += GS_WARPS) {
+      const float* ar = sA + (size_t)i * N;
+      float sa = 0.f;
+      for (int j = lane; j < N; j += 32) sa = fmaf(ar[j], s_sp[j], sa);
+      sa = warp_sum(sa);
+      if (lane == 0) s_sa[i] = sa;
+    }
+    __syncthreads();
+    // ---- scalar GRU gates (GGNN with out_features = 1), one thread per node ----------------------------
+    if (tid < N) {
+      const float wz0 = __ldg(p.gate + 0), bz0 = __ldg(p.gate + 1), wz1 = __ldg(p.gate + 2), bz1 = __ldg(p.gate + 3);
+      const float wr0 = __ldg(p.gate + 4), br0 = __ldg(p.gate + 5), wr1 = __ldg(p.gate + 6), br1 = __ldg(p.gate + 7);
+      const float wh0 = __ldg(p.gate + 8), bh0 = __ldg(p.gate + 9), wh1 = __ldg(p.gate + 10), bh1 = __ldg(p.gate + 11);
+      for (int i = tid; i < N; i += GS_THREADS) {
+        const float sa = s_sa[i], sp = s_sp[i];
+        const float z = sigmoidf_((wz0 * sa + bz0) + (wz1 * sp + bz1));
+        const float r = sigmoidf_((wr0 * sa + br0) + (wr1 * sp + br1));
+        const float h = tanhf((wh0 * sa + bh0) + (wh1 * (r * sp) + bh1));
+        const float sc = h * z + sp * (1.0f - z);
+        s_score[i] = sc;
+        if (p.score) p.score[(int64_t)g * N + i] = sc;
+      }
+    }
+    __syncthreads();
+    // ---- top-k by rank counting (warp per node, ballot + popc); ties -> lower index first --------------
+    for (int i = warp; i < N; i += GS_WARPS) {
+      const float si = s_score[i];
+      int rank = 0;
+      for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        bool ahead = false;
+        if (j < N) {
+          const float sj = s_score[j];
+          ahead = (sj > si) || (sj == si && j < i);
+        }
+        rank += __popc(__ballot_sync(0xffffffffu, ahead));
+      }
+      if (lane == 0) {
+        const uint8_t kp = rank < p.k;
+        s_keep[i] = kp;
+        p.keep_out[(int64_t)g * N + i] = kp;
+      }
+    }
+    // ---- layer-2 dropout draw applied once per element, in place ---------------------------------------
+    if (p.thr) {
+      float4* f4 = reinterpret_cast<float4*>(sF);
+      const uint64_t gbase = (uint64_t)g * N * (uint64_t)H;
+      for (int q = tid; q < N * HQ; q += GS_THREADS) {
+        float4 f = f4[q];
+        const uint64_t base = gbase + (uint64_t)q * 4;
+        f.x = drop_keep(p.seed_2, base + 0, p.thr) ? f.x * p.scale : 0.f;
+        f.y = drop_keep(p.seed_2, base + 1, p.thr) ? f.y * p.scale : 0.f;
+        f.z = drop_keep(p.seed_2, base + 2, p.thr) ? f.z * p.scale : 0.f;
+        f.w = drop_keep(p.seed_2, base + 3, p.thr) ? f.w * p.scale : 0.f;
+        f4[q] = f;
+      }
+    }
+    __syncthreads();
+  } else {
+    if (p.keep_in)
+      for (int i = tid; i < N; i += GS_THREADS) s_keep[i] = p.keep_in[(int64_t)g * N + i];
+    gs_mbar_wait(&bars[0], 0);
+    for (int c = 0; c < GS_CHUNKS; ++c) gs_mbar_wait(&bars[1 + c], 0);
+    __syncthreads();
+  }
+  const bool masked = FUSED || (p.keep_in != nullptr);
+
+  // ---- out[i,:] = sum_j adj'[i,j] * x[j,:]  (one warp per output row, everything from shared memory) ---
+  for (int i = warp; i < N; i += GS_WARPS) {
+    float4 acc[NQ];
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool keep_i = masked ? (s_keep[i] != 0) : true;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      const int j = c0 + lane;
+      float w = 0.f;
+      if (j < N) {
+        w = p.transpose ? sA[(size_t)j * N + i] : sA[(size_t)i * N + j];
+        if (masked && !keep_i && !s_keep[j]) w = 0.f;
+      }
+      unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
+      while (nz) {
+        const int b = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const float wj = __shfl_sync(0xffffffffu, w, b);
+        const float4* row = reinterpret_cast<const float4*>(sF + (size_t)(c0 + b) * H) + lane;
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+          if (u < NQ - 1 || last_ok) {
+            const float4 f = row[u * 32];
+            acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
+            acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
+          }
+        }
+      }
+    }
+    float4* orow = reinterpret_cast<float4*>(gout + (int64_t)i * H) + lane;
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) {
+      if (u < NQ - 1 || last_ok) {
+        float4 v = acc[u];
+        if (p.accumulate) {
+          const float4 o = orow[u * 32];
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        orow[u * 32] = v;
+      }
+    }
+  }
+}
+
+typedef void (*GraphSmemFn)(const GraphParams);
+static GraphSmemFn graph_smem_fn(bool fused, int nq) {
+  switch (nq) {
+    case 1: return fused ? graph_smem_kernel<true, 1> : graph_smem_kernel<false, 1>;
+    case 2: return fused ? graph_smem_kernel<true, 2> : graph_smem_kernel<false, 2>;
+    case 3: return fused ? graph_smem_kernel<true, 3> : graph_smem_kernel<false, 3>;
+    default: return fused ? graph_smem_kernel<true, 4> : graph_smem_kernel<false, 4>;
+  }
+}
+
 __global__ void __launch_bounds__(GRAPH_THREADS) gsl_mask_adj_kernel(const float* __restrict__ adj,
                                                                     const float* __restrict__ score, int N, int k,
                                                                     float* __restrict__ adj_out,
@@ -256,6 +504,30 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
   GETB_REQUIRE(p.G >= 0 && p.N > 0 && p.H > 0, "%s: bad sizes G=%d N=%d H=%d", name, p.G, p.N, p.H);
   GETB_REQUIRE(p.H <= 32 * 4 * MAX_QUADS_PER_LANE, "%s: H=%d exceeds %d", name, p.H, 32 * 4 * MAX_QUADS_PER_LANE);
   if (p.G == 0) return 0;
+  {
+    // fast path: the whole graph (features + adjacency) staged in shared memory by TMA bulk copies
+    const size_t need = ((size_t)p.N * p.H + (size_t)p.N * p.N + 3 * (size_t)p.N) * sizeof(float) +
+                        (((size_t)p.N + 15) & ~(size_t)15) + (GS_CHUNKS + 1) * sizeof(uint64_t);
+    const bool ok = (p.H % 4) == 0 && p.H <= 128 * GS_MAX_QUADS && (p.N % 2) == 0 && aligned16(p.adj) && aligned16(p.x) &&
+                    aligned16(p.out) && (!fused || aligned16(p.wp)) && need <= GS_SMEM_LIMIT &&
+                    (size_t)p.N * p.N * sizeof(float) < (1u << 20) && (size_t)p.N * p.H * sizeof(float) < (1u << 22);
+    if (ok) {
+      const int nq = (p.H / 4 + 31) / 32;
+      GraphSmemFn fn = graph_smem_fn(fused, nq);
+      static bool attr_done[2][GS_MAX_QUADS + 1] = {};
+      if (!attr_done[fused ? 1 : 0][nq]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM_LIMIT) != cudaSuccess) {
+          set_error("%s: cannot opt in to %d bytes of shared memory", name, (int)GS_SMEM_LIMIT);
+          (void)cudaGetLastError();
+          return -2;
+        }
+        attr_done[fused ? 1 : 0][nq] = true;
+      }
+      fn<<<p.G, GS_THREADS, need, st>>>(p);
+      GETB_CHECK_LAUNCH(name);
+      return 0;
+    }
+  }
   p.NP = p.N | 1;
   const size_t tail = (size_t)2 * p.N * sizeof(float) + ((p.N + 15) / 16) * 16;
   size_t smem = (size_t)p.N * p.NP * sizeof(float) + tail;

@@ -72,6 +72,7 @@ TC_ENABLED = os.environ.get("GET_B200_TC", "1") != "0"
 DEBUG_TC_REPORT = False      # tests: record in LAST_GEMM_USED_TC whether the last gemm() ran on the tcgen05 path
 LAST_GEMM_USED_TC = None
 _split_cache = {}
+_SPLIT_CACHE_MAX = 512
 
 
 def split_weight(b: torch.Tensor):
@@ -93,7 +94,11 @@ def split_weight(b: torch.Tensor):
         lo = torch.zeros((N, ldo), dtype=torch.float32, device=b.device)
     _lib.check(lib.get_split_tf32_f32(b.data_ptr(), b.stride(0), b.stride(1), N, K, hi.data_ptr(), lo.data_ptr(), ldo,
                                       _stream()), "get_split_tf32_f32")
-    _split_cache[key] = (ver, hi, lo)
+    # the entry pins the source storage: while it is cached the allocator cannot hand the same address to another
+    # tensor, so (address, shape, strides, version) identifies the weight values exactly
+    _split_cache[key] = (ver, hi, lo, b.untyped_storage())
+    if len(_split_cache) > _SPLIT_CACHE_MAX:
+        _split_cache.pop(next(iter(_split_cache)))
     return hi, lo
 
 
@@ -140,17 +145,18 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
     d.group_rows = group_rows
     d.drop_p, d.drop_seed, d.drop_cols = drop_p, drop_seed & 0xFFFFFFFF, drop_cols
     d.drop_out_p, d.drop_out_seed = drop_out_p, drop_out_seed & 0xFFFFFFFF
+    want_tc = tc and TC_ENABLED and M >= 128
     if split_k is None:
         tiles = ((M + 127) // 128) * ((N + 63) // 64)
         split_k = 1
-        if tiles < _SM_COUNT and ktiles >= 16:
+        if not want_tc and tiles < _SM_COUNT and ktiles >= 16:
             split_k = max(1, min(ktiles // 8, (2 * _SM_COUNT + tiles - 1) // tiles))
     ws = None
     if split_k > 1:
         ws = torch.empty((split_k * M * N,), dtype=torch.float32, device=out.device)
         d.workspace = ws.data_ptr()
     d.split_k = split_k
-    if tc and TC_ENABLED and split_k <= 1 and M >= 64:
+    if want_tc and split_k <= 1:
         keep_alive = []
         for s, (a, b) in enumerate(segments):
             hi, lo = split_weight(b)
