@@ -32,24 +32,38 @@ void count_launch(int n = 1);
   } while (0)
 
 // ---- counter-based dropout ------------------------------------------------------------------
-// keep(seed, i) = (hash32(i32 + seed * 0x9E3779B9) >> 8) >= floor(p * 2^24).  Multipliers are < 2^31 so
-// the host-side mirror (get_b200/dropout.py) can use int64 arithmetic without overflow.
-__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
-  x ^= x >> 16;
-  x *= 0x7feb352dU;
+// One 32-bit hash serves an aligned PAIR of elements (16 bits each):
+//   bits(seed, w) = mix32(lo32(w) * 0x9E3779B1 + hi32(w) * 0x632BE5AB + seed * 0x85EBCA6B + 0x6A09E667),  w = idx >> 1
+//   keep(seed, idx) = ((bits >> (16 * (idx & 1))) & 0xFFFF) >= thr16,   thr16 = floor(p * 65536)
+// so a float4 of 4 consecutive elements (idx % 4 == 0) costs two hashes. get_b200/dropout.py mirrors it on the host.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 15;
   x *= 0x2c1b3c6dU;
-  x ^= x >> 16;
+  x ^= x >> 12;
   x *= 0x297a2d39U;
   x ^= x >> 15;
   return x;
 }
 
-__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)(p * 16777216.0f); }
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)(p * 65536.0f); }
+
+__host__ __device__ __forceinline__ uint32_t drop_bits(uint32_t seed, uint64_t word) {
+  return mix32((uint32_t)word * 0x9E3779B1U + (uint32_t)(word >> 32) * 0x632be5abU + seed * 0x85EBCA6BU + 0x6A09E667U);
+}
 
 __host__ __device__ __forceinline__ bool drop_keep(uint32_t seed, uint64_t idx, uint32_t thr) {
-  uint32_t i32 = (uint32_t)idx + (uint32_t)(idx >> 32) * 0x632be5abU;
-  return (hash32(i32 + seed * 0x9E3779B9U) >> 8) >= thr;
+  const uint32_t b = drop_bits(seed, idx >> 1);
+  return ((b >> (16u * (uint32_t)(idx & 1))) & 0xFFFFu) >= thr;
+}
+
+// 4 consecutive elements starting at idx4 (idx4 % 4 == 0): f <- keep ? f * scale : 0
+__device__ __forceinline__ void drop_apply4(uint32_t seed, uint64_t idx4, uint32_t thr, float scale, float4& f) {
+  const uint32_t b0 = drop_bits(seed, idx4 >> 1);
+  const uint32_t b1 = drop_bits(seed, (idx4 >> 1) + 1);
+  f.x = (b0 & 0xFFFFu) >= thr ? f.x * scale : 0.f;
+  f.y = (b0 >> 16) >= thr ? f.y * scale : 0.f;
+  f.z = (b1 & 0xFFFFu) >= thr ? f.z * scale : 0.f;
+  f.w = (b1 >> 16) >= thr ? f.w * scale : 0.f;
 }
 
 // ---- math -------------------------------------------------------------------------------------

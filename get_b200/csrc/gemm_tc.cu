@@ -206,10 +206,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcC
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint64_t base = (uint64_t)(m0 + r0 + 16 * i) * (uint64_t)p.drop_cols + (uint64_t)k;
-          v[i].x = drop_keep(p.drop_seed, base + 0, p.drop_thr) ? v[i].x * p.drop_scale : 0.f;
-          v[i].y = drop_keep(p.drop_seed, base + 1, p.drop_thr) ? v[i].y * p.drop_scale : 0.f;
-          v[i].z = drop_keep(p.drop_seed, base + 2, p.drop_thr) ? v[i].z * p.drop_scale : 0.f;
-          v[i].w = drop_keep(p.drop_seed, base + 3, p.drop_thr) ? v[i].w * p.drop_scale : 0.f;
+          drop_apply4(p.drop_seed, base, p.drop_thr, p.drop_scale, v[i]);
         }
       }
       mbar_wait(&bar_empty[stage], phase ^ 1);

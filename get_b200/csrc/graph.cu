@@ -232,9 +232,10 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
 // =====================================================================================================
 // Fast path: whole graph resident in shared memory, staged by TMA bulk copies.
 // =====================================================================================================
-constexpr int GS_THREADS = 512;
+constexpr int GS_THREADS = 1024;
 constexpr int GS_WARPS = GS_THREADS / 32;
-constexpr int GS_CHUNKS = 4;            // feature rows arrive in GS_CHUNKS bulk copies, one mbarrier each
+constexpr int GS_MAX_N = 128;           // <= 4 adjacency chunks of 32 columns, <= 4 rows per warp
+constexpr int GS_CHUNKS = GS_MAX_N / 32;  // feature rows arrive in bulk copies of 32 rows, one mbarrier each
 constexpr int GS_MAX_QUADS = 4;         // H <= 32*4*4 = 512 on the fast path
 constexpr size_t GS_SMEM_LIMIT = 226 * 1024;
 
@@ -267,7 +268,8 @@ __device__ __forceinline__ void gs_bulk_g2s(void* dst, const void* src, uint32_t
                : "memory");
 }
 
-// smem layout (floats): [F N*H] [adj N*N] [sp N] [sa N] [score N] | keep N bytes | mbarriers (8-byte aligned)
+// smem layout: [F N*H f32] [L: N*N x 8 B -- the dense adjacency lands in its first half, then per-row neighbour lists
+//              {byte offset of row j in F, weight} overwrite it] [sp N] [score N] [cnt N i32] [rank N i32] [keep N u8] [mbarriers]
 // NQ = ceil(H/4/32): float4 "quads" of a feature row owned by each lane (compile-time so the row loops unroll exactly)
 template <bool FUSED, int NQ>
 __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_constant__ GraphParams p) {
@@ -276,18 +278,20 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, H = p.H, HQ = H >> 2;
   float* sF = smem;
-  float* sA = sF + (size_t)N * H;
-  float* s_sp = sA + (size_t)N * N;
-  float* s_sa = s_sp + N;
-  float* s_score = s_sa + N;
-  uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_score + N);
+  float2* sL = reinterpret_cast<float2*>(sF + (size_t)N * H);      // N*N entries {offset bits, weight}
+  float* sA = reinterpret_cast<float*>(sL);                        // dense adjacency (first half of the list region)
+  float* s_sp = reinterpret_cast<float*>(sL + (size_t)N * N);
+  float* s_score = s_sp + N;
+  int* s_cnt = reinterpret_cast<int*>(s_score + N);
+  int* s_rank = s_cnt + N;
+  uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_rank + N);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_keep + ((N + 15) & ~15));   // [0] adjacency, [1..GS_CHUNKS] features
 
   const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
   const float* __restrict__ gx = p.x + (int64_t)g * N * H;
   float* __restrict__ gout = p.out + (int64_t)g * N * H;
-  const int rows_per_chunk = (N + GS_CHUNKS - 1) / GS_CHUNKS;
   const bool last_ok = (lane + (NQ - 1) * 32) < HQ;   // does this lane own a quad in the last (partial) group?
+  const int nchunks = (N + 31) >> 5;
 
   if (tid == 0) {
     for (int b = 0; b <= GS_CHUNKS; ++b) gs_mbar_init(&bars[b], 1);
@@ -295,49 +299,78 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
   }
   __syncthreads();
   if (tid == 0) {
-    for (int c = 0; c < GS_CHUNKS; ++c) {
-      const int r0 = c * rows_per_chunk;
-      const int r1 = min(N, r0 + rows_per_chunk);
-      if (r1 > r0) {
-        const uint32_t bytes = (uint32_t)(r1 - r0) * (uint32_t)H * 4u;
-        gs_mbar_expect_tx(&bars[1 + c], bytes);
-        gs_bulk_g2s(sF + (size_t)r0 * H, gx + (size_t)r0 * H, bytes, &bars[1 + c]);
-      } else {
-        gs_mbar_expect_tx(&bars[1 + c], 0);
+    const uint32_t abytes = (uint32_t)N * (uint32_t)N * 4u;
+    gs_mbar_expect_tx(&bars[0], abytes);
+    gs_bulk_g2s(sA, gadj, abytes, &bars[0]);
+    for (int c = 0; c < nchunks; ++c) {
+      const int r0 = c * 32;
+      const uint32_t bytes = (uint32_t)(min(N, r0 + 32) - r0) * (uint32_t)H * 4u;
+      gs_mbar_expect_tx(&bars[1 + c], bytes);
+      gs_bulk_g2s(sF + (size_t)r0 * H, gx + (size_t)r0 * H, bytes, &bars[1 + c]);
+    }
+  }
+  if (tid < N) {
+    s_rank[tid] = 0;
+    if (!FUSED) s_keep[tid] = p.keep_in ? p.keep_in[(int64_t)g * N + tid] : (uint8_t)1;
+  }
+
+  // ---- neighbour lists: row i of op(adj) -> {offset of F row j, w_ij}, e < cnt[i] -----------------------------
+  gs_mbar_wait(&bars[0], 0);
+  {
+    float wv[4][4];   // [row slot][column chunk]
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = warp + r * GS_WARPS;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = c * 32 + lane;
+        wv[r][c] = (i < N && j < N) ? (p.transpose ? sA[(size_t)j * N + i] : sA[(size_t)i * N + j]) : 0.f;
       }
-      if (c == 0) {
-        const uint32_t abytes = (uint32_t)N * (uint32_t)N * 4u;
-        gs_mbar_expect_tx(&bars[0], abytes);
-        gs_bulk_g2s(sA, gadj, abytes, &bars[0]);
+    }
+    __syncthreads();   // every row is in registers before the lists overwrite the dense tile
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = warp + r * GS_WARPS;
+      if (i < N) {
+        int pos = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const unsigned nz = __ballot_sync(0xffffffffu, wv[r][c] != 0.f);
+          if (wv[r][c] != 0.f) {
+            const int e = pos + __popc(nz & ((1u << lane) - 1u));
+            sL[(size_t)i * N + e] = make_float2(__int_as_float((c * 32 + lane) * H * 4), wv[r][c]);
+          }
+          pos += __popc(nz);
+        }
+        if (lane == 0) s_cnt[i] = pos;
       }
     }
   }
 
   if (FUSED) {
-    // ---- s_p[i] = drop_s(F[i,:]) . wp  (warp per row, chunk by chunk as the copies land) --------------
+    // ---- s_p[i] = drop_s(F[i,:]) . wp ; the layer-2 dropout draw is applied in place on the way ----------------
     float4 wq[NQ];
 #pragma unroll
     for (int u = 0; u < NQ; ++u) {
       const int q = lane + u * 32;
       wq[u] = q < HQ ? __ldg(reinterpret_cast<const float4*>(p.wp) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int c = 0; c < GS_CHUNKS; ++c) {
+    for (int c = 0; c < nchunks; ++c) {
       gs_mbar_wait(&bars[1 + c], 0);
-      const int r1 = min(N, (c + 1) * rows_per_chunk);
-      for (int i = c * rows_per_chunk + warp; i < r1; i += GS_WARPS) {
-        const float4* row = reinterpret_cast<const float4*>(sF + (size_t)i * H);
+      const int i = c * 32 + warp;
+      if (i < N) {
+        float4* row = reinterpret_cast<float4*>(sF + (size_t)i * H) + lane;
         float acc = 0.f;
 #pragma unroll
         for (int u = 0; u < NQ; ++u) {
           if (u < NQ - 1 || last_ok) {
-            const int q = lane + u * 32;
-            float4 f = row[q];
+            float4 f = row[u * 32];
             if (p.thr) {
-              const uint64_t base = ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)q * 4;
-              f.x = drop_keep(p.seed_s, base + 0, p.thr) ? f.x * p.scale : 0.f;
-              f.y = drop_keep(p.seed_s, base + 1, p.thr) ? f.y * p.scale : 0.f;
-              f.z = drop_keep(p.seed_s, base + 2, p.thr) ? f.z * p.scale : 0.f;
-              f.w = drop_keep(p.seed_s, base + 3, p.thr) ? f.w * p.scale : 0.f;
+              const uint64_t base = ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)(lane + u * 32) * 4;
+              float4 f2 = f;
+              drop_apply4(p.seed_2, base, p.thr, p.scale, f2);
+              row[u * 32] = f2;
+              drop_apply4(p.seed_s, base, p.thr, p.scale, f);
             }
             acc = fmaf(f.x, wq[u].x, acc); acc = fmaf(f.y, wq[u].y, acc);
             acc = fmaf(f.z, wq[u].z, acc); acc = fmaf(f.w, wq[u].w, acc);
@@ -347,102 +380,88 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
         if (lane == 0) s_sp[i] = acc;
       }
     }
-    gs_mbar_wait(&bars[0], 0);
     __syncthreads();
-    // ---- s_a = adj @ s_p (warp per row) ---------------------------------------------------------------
-    for (int i = warp; i < N; i += GS_WARPS) {
-      const float* ar = sA + (size_t)i * N;
-      float sa = 0.f;
-      for (int j = lane; j < N; j += 32) sa = fmaf(ar[j], s_sp[j], sa);
-      sa = warp_sum(sa);
-      if (lane == 0) s_sa[i] = sa;
-    }
-    __syncthreads();
-    // ---- scalar GRU gates (GGNN with out_features = 1), one thread per node ----------------------------
+    // ---- s_a = adj @ s_p over the neighbour lists + scalar GRU gates (GGNN with out_features = 1) --------------
     if (tid < N) {
+      const int i = tid;
+      const float2* lr = sL + (size_t)i * N;
+      const int cnt = s_cnt[i];
+      const float inv_rowbytes = 1.0f / (float)(H * 4);   // offsets are exact multiples of H*4 < 2^24: rounding recovers j
+      float sa = 0.f;
+      for (int e = 0; e < cnt; ++e) {
+        const float2 en = lr[e];
+        sa = fmaf(en.y, s_sp[__float2int_rn(__int2float_rn(__float_as_int(en.x)) * inv_rowbytes)], sa);
+      }
       const float wz0 = __ldg(p.gate + 0), bz0 = __ldg(p.gate + 1), wz1 = __ldg(p.gate + 2), bz1 = __ldg(p.gate + 3);
       const float wr0 = __ldg(p.gate + 4), br0 = __ldg(p.gate + 5), wr1 = __ldg(p.gate + 6), br1 = __ldg(p.gate + 7);
       const float wh0 = __ldg(p.gate + 8), bh0 = __ldg(p.gate + 9), wh1 = __ldg(p.gate + 10), bh1 = __ldg(p.gate + 11);
-      for (int i = tid; i < N; i += GS_THREADS) {
-        const float sa = s_sa[i], sp = s_sp[i];
-        const float z = sigmoidf_((wz0 * sa + bz0) + (wz1 * sp + bz1));
-        const float r = sigmoidf_((wr0 * sa + br0) + (wr1 * sp + br1));
-        const float h = tanhf((wh0 * sa + bh0) + (wh1 * (r * sp) + bh1));
-        const float sc = h * z + sp * (1.0f - z);
-        s_score[i] = sc;
-        if (p.score) p.score[(int64_t)g * N + i] = sc;
+      const float sp = s_sp[i];
+      const float z = sigmoidf_((wz0 * sa + bz0) + (wz1 * sp + bz1));
+      const float r = sigmoidf_((wr0 * sa + br0) + (wr1 * sp + br1));
+      const float h = tanhf((wh0 * sa + bh0) + (wh1 * (r * sp) + bh1));
+      const float sc = h * z + sp * (1.0f - z);
+      s_score[i] = sc;
+      if (p.score) p.score[(int64_t)g * N + i] = sc;
+    }
+    __syncthreads();
+    // ---- top-k by rank counting: thread (node i, slice of 16 candidates), partial ranks added in shared memory;
+    //      ties -> lower index first -----------------------------------------------------------------------------
+    {
+      const int i = tid & (GS_MAX_N - 1);
+      const int j0 = (tid >> 7) * (GS_MAX_N / (GS_THREADS / GS_MAX_N));   // 8 slices of 16
+      if (i < N && j0 < N) {
+        const float si = s_score[i];
+        const int j1 = min(N, j0 + GS_MAX_N / (GS_THREADS / GS_MAX_N));
+        int rank = 0;
+        for (int j = j0; j < j1; ++j) {
+          const float sj = s_score[j];
+          rank += ((sj > si) || (sj == si && j < i)) ? 1 : 0;
+        }
+        if (rank) atomicAdd(&s_rank[i], rank);
       }
     }
     __syncthreads();
-    // ---- top-k by rank counting (warp per node, ballot + popc); ties -> lower index first --------------
-    for (int i = warp; i < N; i += GS_WARPS) {
-      const float si = s_score[i];
-      int rank = 0;
-      for (int j0 = 0; j0 < N; j0 += 32) {
-        const int j = j0 + lane;
-        bool ahead = false;
-        if (j < N) {
-          const float sj = s_score[j];
-          ahead = (sj > si) || (sj == si && j < i);
-        }
-        rank += __popc(__ballot_sync(0xffffffffu, ahead));
-      }
-      if (lane == 0) {
-        const uint8_t kp = rank < p.k;
-        s_keep[i] = kp;
-        p.keep_out[(int64_t)g * N + i] = kp;
-      }
-    }
-    // ---- layer-2 dropout draw applied once per element, in place ---------------------------------------
-    if (p.thr) {
-      float4* f4 = reinterpret_cast<float4*>(sF);
-      const uint64_t gbase = (uint64_t)g * N * (uint64_t)H;
-      for (int q = tid; q < N * HQ; q += GS_THREADS) {
-        float4 f = f4[q];
-        const uint64_t base = gbase + (uint64_t)q * 4;
-        f.x = drop_keep(p.seed_2, base + 0, p.thr) ? f.x * p.scale : 0.f;
-        f.y = drop_keep(p.seed_2, base + 1, p.thr) ? f.y * p.scale : 0.f;
-        f.z = drop_keep(p.seed_2, base + 2, p.thr) ? f.z * p.scale : 0.f;
-        f.w = drop_keep(p.seed_2, base + 3, p.thr) ? f.w * p.scale : 0.f;
-        f4[q] = f;
-      }
+    if (tid < N) {
+      const uint8_t kp = s_rank[tid] < p.k;
+      s_keep[tid] = kp;
+      p.keep_out[(int64_t)g * N + tid] = kp;
     }
     __syncthreads();
   } else {
-    if (p.keep_in)
-      for (int i = tid; i < N; i += GS_THREADS) s_keep[i] = p.keep_in[(int64_t)g * N + i];
-    gs_mbar_wait(&bars[0], 0);
-    for (int c = 0; c < GS_CHUNKS; ++c) gs_mbar_wait(&bars[1 + c], 0);
+    for (int c = 0; c < nchunks; ++c) gs_mbar_wait(&bars[1 + c], 0);
     __syncthreads();
   }
-  const bool masked = FUSED || (p.keep_in != nullptr);
 
-  // ---- out[i,:] = sum_j adj'[i,j] * x[j,:]  (one warp per output row, everything from shared memory) ---
+  // ---- out[i,:] = sum_e w[i][e] * x[idx[i][e],:]  (one warp per output row, everything from shared memory) ---
+  const bool masked = FUSED || (p.keep_in != nullptr);
+  const char* sFb = reinterpret_cast<const char*>(sF) + lane * 16;
+  const float inv_rowbytes = 1.0f / (float)(H * 4);
   for (int i = warp; i < N; i += GS_WARPS) {
     float4 acc[NQ];
 #pragma unroll
     for (int u = 0; u < NQ; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool keep_i = masked ? (s_keep[i] != 0) : true;
-    for (int c0 = 0; c0 < N; c0 += 32) {
-      const int j = c0 + lane;
-      float w = 0.f;
-      if (j < N) {
-        w = p.transpose ? sA[(size_t)j * N + i] : sA[(size_t)i * N + j];
-        if (masked && !keep_i && !s_keep[j]) w = 0.f;
+    float2* lr = sL + (size_t)i * N;
+    const int cnt = s_cnt[i];
+    if (masked && s_keep[i] == 0) {   // a dropped node keeps only its edges to kept nodes (wrapper.py:221-225)
+      for (int e = lane; e < cnt; e += 32) {
+        const float2 en = lr[e];
+        const int j = __float2int_rn(__int2float_rn(__float_as_int(en.x)) * inv_rowbytes);
+        if (!s_keep[j]) lr[e].y = 0.f;
       }
-      unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
-      while (nz) {
-        const int b = __ffs(nz) - 1;
-        nz &= nz - 1;
-        const float wj = __shfl_sync(0xffffffffu, w, b);
-        const float4* row = reinterpret_cast<const float4*>(sF + (size_t)(c0 + b) * H) + lane;
+      __syncwarp();
+    }
+#pragma unroll 2
+    for (int e = 0; e < cnt; ++e) {
+      const float2 en = lr[e];
+      const int off = __float_as_int(en.x);
+      const float wj = en.y;
+      const float4* row = reinterpret_cast<const float4*>(sFb + off);
 #pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-          if (u < NQ - 1 || last_ok) {
-            const float4 f = row[u * 32];
-            acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
-            acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
-          }
+      for (int u = 0; u < NQ; ++u) {
+        if (u < NQ - 1 || last_ok) {
+          const float4 f = row[u * 32];
+          acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
+          acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
         }
       }
     }
@@ -506,11 +525,10 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
   if (p.G == 0) return 0;
   {
     // fast path: the whole graph (features + adjacency) staged in shared memory by TMA bulk copies
-    const size_t need = ((size_t)p.N * p.H + (size_t)p.N * p.N + 3 * (size_t)p.N) * sizeof(float) +
+    const size_t need = ((size_t)p.N * p.H + 2 * (size_t)p.N * p.N + 4 * (size_t)p.N) * sizeof(float) +
                         (((size_t)p.N + 15) & ~(size_t)15) + (GS_CHUNKS + 1) * sizeof(uint64_t);
-    const bool ok = (p.H % 4) == 0 && p.H <= 128 * GS_MAX_QUADS && (p.N % 2) == 0 && aligned16(p.adj) && aligned16(p.x) &&
-                    aligned16(p.out) && (!fused || aligned16(p.wp)) && need <= GS_SMEM_LIMIT &&
-                    (size_t)p.N * p.N * sizeof(float) < (1u << 20) && (size_t)p.N * p.H * sizeof(float) < (1u << 22);
+    const bool ok = (p.H % 4) == 0 && p.H <= 128 * GS_MAX_QUADS && (p.N % 2) == 0 && p.N <= GS_MAX_N && aligned16(p.adj) &&
+                    aligned16(p.x) && aligned16(p.out) && (!fused || aligned16(p.wp)) && need <= GS_SMEM_LIMIT;
     if (ok) {
       const int nq = (p.H / 4 + 31) / 32;
       GraphSmemFn fn = graph_smem_fn(fused, nq);
