@@ -436,11 +436,17 @@ int gemm_tc_launch(const get_gemm_desc* d, const GemmParams& p, cudaStream_t st)
 
 using namespace getb;
 
+int getb::gemm_tc_eligible(const get_gemm_desc* d, const GemmParams& p) {
+  TcCfg cfg;
+  return tc_plan(d, p, cfg) == 0 ? 1 : 0;
+}
+
 extern "C" int get_gemm_f32_uses_tc(const get_gemm_desc* d) {
   GemmParams p;
   if (gemm_build_params(d, p) != 0) return -1;
-  TcCfg cfg;
-  return tc_plan(d, p, cfg) == 0 ? 1 : 0;
+  if (p.M == 0 || p.N == 0) return 0;
+  if (gemm_tc2_plan_splits(d, p) > 0) return 2;
+  return gemm_tc_eligible(d, p);
 }
 
 extern "C" int get_split_tf32_f32(const float* src, int64_t ld_r, int64_t ld_c, int rows, int cols, float* hi,

@@ -1,0 +1,559 @@
+// Persistent, warp-specialised tcgen05 contraction with fp32-level accuracy (error-compensated 3xTF32) for the dense
+// `Linear`s of the GET hot path and their backward passes (reference Models/BiDAF/wrapper.py:191,194-204;
+// thirdparty/two_branches_attention.py:140; autograd of both).
+//
+//   acc = A_hi.B_hi  (main accumulator)  +  A_hi.B_lo + A_lo.B_hi  (separate "small" accumulator, summed in the epilogue
+//   so the tensor core's truncating fp32 accumulation only ever sees terms of like magnitude)
+//
+// Every operand tile is brought in by TMA (cp.async.bulk.tensor, SWIZZLE_128B) as raw fp32:
+//   * K-major operands (activations (M,K) row-major; pre-split weights (N,K)): one box {32 k, rows};
+//   * MN-major operands (the weight-gradient contraction dW = dG^T . X, both operands (K,MN) row-major): boxes
+//     {32 mn, 32 k} (TMA swizzle 128B_ATOM_32B), consumed through MN-major UMMA descriptors (SWIZZLE_128B_BASE32B, the
+//     only MN-major layout fp32 operands have) -- no transposition pass anywhere.
+// Warp roles (320 threads, one persistent CTA per SM, static round-robin over work items):
+//   warp 0      TMA producer                         warp 1      tcgen05.mma issuer, owns the TMEM allocation
+//   warps 2-5   splitter: raw tile -> hi (tf32 round-to-nearest, in place) + lo (second buffer), smem -> smem
+//   warps 6-9   epilogue: tcgen05.ld main+small -> fused epilogue (gemm_common.cuh) -> global; with two TMEM
+//               accumulator sets the epilogue of item i overlaps the main loop of item i+1
+// Work item = (m tile, n tile, k split); split-K items store raw partial tiles that gemm_splitk_reduce_kernel sums in
+// a fixed order (deterministic weight gradients).
+#include <cuda.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_common.cuh"
+
+namespace getb {
+
+constexpr int T2_BM = 128;
+constexpr int T2_BK = 32;
+constexpr int T2_THREADS = 320;
+constexpr int T2_A_TILE = T2_BM * 128;   // bytes of one A tile (hi or lo)
+constexpr int T2_MAX_STAGES = 4;
+constexpr uint32_t T2_SPIN_LIMIT = 1u << 28;
+
+struct Tc2Maps {
+  CUtensorMap a[GET_GEMM_MAX_SEG];
+  CUtensorMap bh[GET_GEMM_MAX_SEG];
+  CUtensorMap bl[GET_GEMM_MAX_SEG];
+};
+
+struct Tc2Cfg {
+  int BN, stages, acc_bufs, tmem_cols;
+  int kblocks[GET_GEMM_MAX_SEG];
+  int kblocks_total;
+  int a_mn, b_mn;        // operand is MN-major (stored (K, MN) row-major)
+  int split_b;           // B arrives raw and is split in the kernel (otherwise B_hi / B_lo are loaded pre-split)
+  int ntm, ntn, splits, kb_per_split, items;
+  uint32_t b_tile, stage_bytes;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+namespace t2 {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > T2_SPIN_LIMIT) __trap();   // a protocol bug must fail loudly, never hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory operand descriptor.
+// K-major, SWIZZLE_128B (layout type 2): rows at a 128-byte pitch, 8-row groups `sbo` = 1024 B apart, LBO unused.
+// MN-major fp32/tf32 operands only exist as SWIZZLE_128B_BASE32B (layout type 1; the TMA mode is 128B_ATOM_32B):
+// 128-byte rows of 32 MN elements, 4-k groups `sbo` = 512 B apart, 32-element MN groups `lbo` bytes apart.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t f32_to_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+}  // namespace t2
+
+// locate k-block `kb` (global index over the segments): segment and k offset inside it
+__device__ __forceinline__ void t2_locate(const Tc2Cfg& cfg, int nseg, int kb, int& seg, int& kin) {
+  seg = 0;
+  while (seg + 1 < nseg && kb >= cfg.kblocks[seg]) { kb -= cfg.kblocks[seg]; ++seg; }
+  kin = kb * T2_BK;
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc2Cfg cfg, const __grid_constant__ Tc2Maps maps) {
+  using namespace t2;
+  extern __shared__ __align__(1024) uint8_t smem_raw2[];
+  __shared__ __align__(8) uint64_t bar_raw[T2_MAX_STAGES];     // TMA landed (tx bytes)
+  __shared__ __align__(8) uint64_t bar_ready[T2_MAX_STAGES];   // hi/lo tiles complete (128 splitter arrivals)
+  __shared__ __align__(8) uint64_t bar_empty[T2_MAX_STAGES];   // MMAs that read the stage retired (tcgen05.commit)
+  __shared__ __align__(8) uint64_t bar_accf[2];                // accumulator set complete (tcgen05.commit)
+  __shared__ __align__(8) uint64_t bar_acce[2];                // accumulator set drained (128 epilogue arrivals)
+  __shared__ uint32_t tmem_holder;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = cfg.BN;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (tid == 0) {
+    for (int s = 0; s < cfg.stages; ++s) {
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_ready[s], 128);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_accf[b], 1);
+      mbar_init(&bar_acce[b], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                 "r"((uint32_t)cfg.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  const int n_my = ((int)blockIdx.x < cfg.items) ? (cfg.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    // =========================================== TMA producer ===========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = T2_A_TILE;
+      const uint32_t tx = a_bytes + cfg.b_tile * (cfg.split_b ? 1u : 2u);
+      for (int it = 0; it < n_my; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int nt = item % cfg.ntn, mt = (item / cfg.ntn) % cfg.ntm, z = item / (cfg.ntn * cfg.ntm);
+        const int m0 = mt * T2_BM, n0 = nt * BN;
+        const int kb0 = z * cfg.kb_per_split, kb1 = min(cfg.kblocks_total, kb0 + cfg.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          int seg, kin;
+          t2_locate(cfg, p.nseg, kb, seg, kin);
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          const uint32_t sa = smem_base + (uint32_t)stage * cfg.stage_bytes;
+          const uint32_t sbh = sa + 2u * T2_A_TILE, sbl = sbh + cfg.b_tile;
+          mbar_arrive_expect_tx(&bar_raw[stage], tx);
+          if (cfg.a_mn) {
+#pragma unroll
+            for (int a = 0; a < T2_BM / 32; ++a) tma_load_2d(sa + a * 4096u, &maps.a[seg], m0 + a * 32, kin, &bar_raw[stage]);
+          } else {
+            tma_load_2d(sa, &maps.a[seg], kin, m0, &bar_raw[stage]);
+          }
+          if (cfg.b_mn) {
+            for (int a = 0; a < BN / 32; ++a) tma_load_2d(sbh + a * 4096u, &maps.bh[seg], n0 + a * 32, kin, &bar_raw[stage]);
+          } else {
+            tma_load_2d(sbh, &maps.bh[seg], kin, n0, &bar_raw[stage]);
+            if (!cfg.split_b) tma_load_2d(sbl, &maps.bl[seg], kin, n0, &bar_raw[stage]);
+          }
+          if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================================== MMA issuer =============================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cfg.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(cfg.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(T2_BM >> 4) << 24);
+      const uint32_t a_step = cfg.a_mn ? 1024u : 32u;     // bytes per 8-k step
+      const uint32_t b_step = cfg.b_mn ? 1024u : 32u;
+      const uint32_t a_lbo = cfg.a_mn ? 4096u : 16u, b_lbo = cfg.b_mn ? 4096u : 16u;
+      const uint32_t a_sbo = cfg.a_mn ? 512u : 1024u, b_sbo = cfg.b_mn ? 512u : 1024u;
+      const uint32_t a_lt = cfg.a_mn ? 1u : 2u, b_lt = cfg.b_mn ? 1u : 2u;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int z = item / (cfg.ntn * cfg.ntm);
+        const int kb0 = z * cfg.kb_per_split, kb1 = min(cfg.kblocks_total, kb0 + cfg.kb_per_split);
+        mbar_wait(&bar_acce[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * BN);
+        const uint32_t d_small = d_main + (uint32_t)BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bar_raw[stage], phase);
+          mbar_wait(&bar_ready[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + (uint32_t)stage * cfg.stage_bytes;
+          const uint32_t a_lo = a_hi + T2_A_TILE;
+          const uint32_t b_hi = a_lo + T2_A_TILE;
+          const uint32_t b_lo = b_hi + cfg.b_tile;
+#pragma unroll
+          for (int ks = 0; ks < T2_BK / 8; ++ks) {
+            const uint64_t dah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t dbh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt), dbl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+            const uint32_t first = (kb > kb0 || ks > 0) ? 1u : 0u;
+            umma_tf32(d_main, dah, dbh, idesc, first);
+            umma_tf32(d_small, dah, dbl, idesc, first);
+            umma_tf32(d_small, dal, dbh, idesc, 1u);
+          }
+          umma_commit(&bar_empty[stage]);
+          if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bar_accf[acc]);
+        if (cfg.acc_bufs == 2) {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        } else {
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // =========================================== splitter ===============================================
+    const int t = tid - 64;   // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    const int a_chunks = T2_A_TILE / 16 / 128;                       // 16-byte chunks per thread in the A tile
+    const int b_chunks = cfg.split_b ? (int)(cfg.b_tile / 16) : 0;   // total chunks of the B tile
+    for (int it = 0; it < n_my; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int z = item / (cfg.ntn * cfg.ntm);
+      const int kb0 = z * cfg.kb_per_split, kb1 = min(cfg.kblocks_total, kb0 + cfg.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&bar_raw[stage], phase);
+        uint8_t* a_hi = smem + (size_t)stage * cfg.stage_bytes;
+        uint8_t* a_lo = a_hi + T2_A_TILE;
+#pragma unroll
+        for (int i = 0; i < a_chunks; ++i) {
+          const uint32_t off = (uint32_t)(t + i * 128) * 16u;
+          const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+          uint4 hi, lo;
+          hi.x = f32_to_tf32_rn(v.x); hi.y = f32_to_tf32_rn(v.y); hi.z = f32_to_tf32_rn(v.z); hi.w = f32_to_tf32_rn(v.w);
+          lo.x = f32_to_tf32_rn(v.x - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rn(v.y - __uint_as_float(hi.y));
+          lo.z = f32_to_tf32_rn(v.z - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rn(v.w - __uint_as_float(hi.w));
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        }
+        if (cfg.split_b) {
+          uint8_t* b_hi = a_lo + T2_A_TILE;
+          uint8_t* b_lo = b_hi + cfg.b_tile;
+          for (int c = t; c < b_chunks; c += 128) {
+            const uint32_t off = (uint32_t)c * 16u;
+            const float4 v = *reinterpret_cast<const float4*>(b_hi + off);
+            uint4 hi, lo;
+            hi.x = f32_to_tf32_rn(v.x); hi.y = f32_to_tf32_rn(v.y); hi.z = f32_to_tf32_rn(v.z); hi.w = f32_to_tf32_rn(v.w);
+            lo.x = f32_to_tf32_rn(v.x - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rn(v.y - __uint_as_float(hi.y));
+            lo.z = f32_to_tf32_rn(v.z - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rn(v.w - __uint_as_float(hi.w));
+            *reinterpret_cast<uint4*>(b_hi + off) = hi;
+            *reinterpret_cast<uint4*>(b_lo + off) = lo;
+          }
+        }
+        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&bar_ready[stage]);
+        if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // =========================================== epilogue ===============================================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int nt = item % cfg.ntn, mt = (item / cfg.ntn) % cfg.ntm, z = item / (cfg.ntn * cfg.ntm);
+      const int m = mt * T2_BM + quarter * 32 + lane;
+      const int n0 = nt * BN;
+      mbar_wait(&bar_accf[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN);
+      const uint32_t t_small = t_main + (uint32_t)BN;
+      for (int col = 0; col < BN; col += 16) {
+        uint32_t rm[16], rs[16];
+        tmem_ld16_nowait(t_main + (uint32_t)col, rm);
+        tmem_ld16_nowait(t_small + (uint32_t)col, rs);
+        tmem_ld_wait();
+        if (m < p.M) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = n0 + col + q * 4;
+            if (n < p.N) {
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(rm[q * 4 + e]) + __uint_as_float(rs[q * 4 + e]);
+              if (cfg.splits > 1) {
+                store4(p.workspace + ((int64_t)z * p.M + m) * p.N + n, (p.N & 3) == 0, min(4, p.N - n), v);
+              } else {
+                epilogue4(p, m, n, v);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_acce[acc]);
+      if (cfg.acc_bufs == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn2 t2_encode_fn() {
+  static EncodeTiledFn2 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn2>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements per row, `outer` rows `ld` elements apart; box {box_inner, box_outer}
+struct T2MapKey {
+  const float* ptr;
+  int64_t inner, outer, ld;
+  int bi, bo, mn;
+  bool operator==(const T2MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && bi == o.bi && bo == o.bo && mn == o.mn;
+  }
+};
+struct T2MapKeyHash {
+  size_t operator()(const T2MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+    h ^= (uint64_t)k.inner * 0xC2B2AE3D27D4EB4Full + (uint64_t)k.outer * 0x165667B19E3779F9ull + (uint64_t)k.ld * 31 +
+         (uint64_t)k.bi * 7 + (uint64_t)k.bo + (uint64_t)k.mn * 1315423911ull;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+
+static bool t2_encode(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                      int box_outer, int mn);
+
+// Tensor maps depend only on (address, extents, stride, box): encoding is memoised because the allocator hands the same
+// activation addresses back step after step.
+static bool t2_make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                        int box_outer, int mn) {
+  static std::mutex mu;
+  static std::unordered_map<T2MapKey, CUtensorMap, T2MapKeyHash> cache;
+  const T2MapKey key{ptr, inner, outer, ld, box_inner, box_outer, mn};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *map = it->second;
+    return true;
+  }
+  if (!t2_encode(map, ptr, inner, outer, ld, box_inner, box_outer, mn)) return false;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *map);
+  return true;
+}
+
+static bool t2_encode(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                      int box_outer, int mn) {
+  EncodeTiledFn2 enc = t2_encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int t2_pad(int n, int q) { return (n + q - 1) / q * q; }
+
+// 0 = eligible (cfg filled), 1 = not eligible
+static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
+  if (d->tc_mode < 1) return 1;
+  if (p.M < 1 || p.N < 8) return 1;
+  if (p.drop_thr) return 1;                                   // A-operand dropout: register-staged kernel (gemm_tc.cu)
+  memset(&cfg, 0, sizeof(cfg));
+  const bool presplit = d->B_hi[0] != nullptr;
+  cfg.a_mn = p.A[0].trans;
+  cfg.b_mn = presplit ? 0 : p.B[0].trans;
+  cfg.split_b = presplit ? 0 : 1;
+  for (int s = 0; s < p.nseg; ++s) {
+    if (p.A[s].rowidx) return 1;                              // gathered A: register-staged kernel
+    if (p.A[s].trans != cfg.a_mn || !aligned16(p.A[s].ptr) || (p.A[s].ld % 4) != 0) return 1;
+    if (presplit) {
+      if (!d->B_hi[s] || !d->B_lo[s] || !aligned16(d->B_hi[s]) || !aligned16(d->B_lo[s]) || (d->ld_split[s] % 4) != 0 ||
+          d->ld_split[s] < p.K[s])
+        return 1;
+    } else {
+      if (d->B_hi[s] || p.B[s].trans != cfg.b_mn || !aligned16(p.B[s].ptr) || (p.B[s].ld % 4) != 0) return 1;
+    }
+    if (p.K[s] < 8) return 1;
+    cfg.kblocks[s] = (p.K[s] + T2_BK - 1) / T2_BK;
+    cfg.kblocks_total += cfg.kblocks[s];
+  }
+  cfg.ntm = (p.M + T2_BM - 1) / T2_BM;
+  const int q = cfg.b_mn ? 32 : 16;                           // MN-major B tiles are built from 32-wide boxes
+  // split-K (host decides through desc->split_k; p.split_k was clamped against 16-wide SIMT k tiles, redo it here)
+  int splits = d->split_k > 1 ? d->split_k : 1;
+  if (splits > cfg.kblocks_total) splits = cfg.kblocks_total;
+  cfg.kb_per_split = (cfg.kblocks_total + splits - 1) / splits;
+  cfg.splits = (cfg.kblocks_total + cfg.kb_per_split - 1) / cfg.kb_per_split;
+  if (cfg.splits > 1 && !d->workspace) return 1;
+  // n tiling: two accumulator sets (main + small) x two buffers must fit 512 TMEM columns when the CTA handles several items
+  int best_nt = 0;
+  double best_cost = 1e30;
+  for (int nt = 1; nt <= 8; ++nt) {
+    const int bn = t2_pad((p.N + nt - 1) / nt, q);
+    if (bn > 256 || bn < 16) continue;
+    if ((nt - 1) * bn >= p.N) continue;
+    const int64_t items = (int64_t)cfg.ntm * nt * cfg.splits;
+    const int64_t rounds = (items + 147) / 148;
+    if (rounds > 1 && bn > 128) continue;                     // double-buffered accumulators need 4*bn <= 512
+    const double cost = (double)rounds * (bn + 48.0);
+    if (cost < best_cost) { best_cost = cost; best_nt = nt; }
+  }
+  if (best_nt == 0) return 1;
+  if (d->tc_n_tiles > 0) {
+    const int bn = t2_pad((p.N + d->tc_n_tiles - 1) / d->tc_n_tiles, q);
+    if (bn <= 128 && bn >= 16 && (d->tc_n_tiles - 1) * bn < p.N) best_nt = d->tc_n_tiles;
+  }
+  cfg.ntn = best_nt;
+  cfg.BN = t2_pad((p.N + best_nt - 1) / best_nt, q);
+  cfg.items = cfg.ntm * cfg.ntn * cfg.splits;
+  cfg.acc_bufs = (4 * cfg.BN <= 512) ? 2 : 1;
+  int tc = 32;
+  while (tc < cfg.acc_bufs * 2 * cfg.BN) tc <<= 1;
+  if (tc > 512) return 1;
+  cfg.tmem_cols = tc;
+  cfg.b_tile = (uint32_t)cfg.BN * 128u;
+  cfg.stage_bytes = 2u * T2_A_TILE + 2u * cfg.b_tile;
+  int stages = (224 * 1024 - 2048) / (int)cfg.stage_bytes;
+  if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
+  if (stages < 2) return 1;
+  cfg.stages = stages;
+  return 0;
+}
+
+int gemm_tc2_launch(const get_gemm_desc* d, GemmParams& p, cudaStream_t st) {
+  Tc2Cfg cfg;
+  if (tc2_plan(d, p, cfg) != 0) return 1;
+  p.split_k = cfg.splits;
+  Tc2Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int s = 0; s < p.nseg; ++s) {
+    bool ok;
+    if (cfg.a_mn) ok = t2_make_map(&maps.a[s], p.A[s].ptr, p.M, p.K[s], p.A[s].ld, 32, T2_BK, 1);
+    else ok = t2_make_map(&maps.a[s], p.A[s].ptr, p.K[s], p.M, p.A[s].ld, T2_BK, T2_BM, 0);
+    if (!ok) return 1;
+    if (!cfg.split_b) {
+      if (!t2_make_map(&maps.bh[s], d->B_hi[s], p.K[s], p.N, d->ld_split[s], T2_BK, cfg.BN, 0)) return 1;
+      if (!t2_make_map(&maps.bl[s], d->B_lo[s], p.K[s], p.N, d->ld_split[s], T2_BK, cfg.BN, 0)) return 1;
+    } else if (cfg.b_mn) {
+      if (!t2_make_map(&maps.bh[s], p.B[s].ptr, p.N, p.K[s], p.B[s].ld, 32, T2_BK, 1)) return 1;
+    } else {
+      if (!t2_make_map(&maps.bh[s], p.B[s].ptr, p.K[s], p.N, p.B[s].ld, T2_BK, cfg.BN, 0)) return 1;
+    }
+  }
+  const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + 1024;
+  static int max_dyn = -1;
+  if (max_dyn < 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tc2_kernel);
+    if (e == cudaSuccess) {
+      const int want = 227 * 1024 - (int)((fa.sharedSizeBytes + 1023) / 1024 * 1024);
+      e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      if (e == cudaSuccess) max_dyn = want;
+    }
+    if (e != cudaSuccess) {
+      set_error("gemm_tc2_kernel: cannot opt in to large shared memory: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return -(int)e - 1000;
+    }
+  }
+  if ((int)smem > max_dyn) return 1;
+  const int grid = cfg.items < 148 ? cfg.items : 148;
+  gemm_tc2_kernel<<<grid, T2_THREADS, smem, st>>>(p, cfg, maps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("gemm_tc2_kernel: launch failed: %s", cudaGetErrorString(e));
+    return -(int)e - 1000;
+  }
+  count_launch();
+  return cfg.splits > 1 ? 2 : 0;   // 2: caller must run the split-K reduction with p.split_k = cfg.splits
+}
+
+int gemm_tc2_plan_splits(const get_gemm_desc* d, const GemmParams& p) {
+  Tc2Cfg cfg;
+  if (tc2_plan(d, p, cfg) != 0) return -1;
+  return cfg.splits;
+}
+
+}  // namespace getb

@@ -111,9 +111,10 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
          bias0=None, bias1=None, aux0=None, aux1=None, out1=None, group_rows: int = 0, alpha: float = 1.0,
          accumulate: bool = False, rowidx: Optional[torch.Tensor] = None, drop_p: float = 0.0, drop_seed: int = 0,
          drop_cols: int = 0, drop_out_p: float = 0.0, drop_out_seed: int = 0, split_k: Optional[int] = None,
-         tc: bool = False, tc_n_tiles: int = 0):
+         tc: bool = False, tc_n_tiles: int = 0, presplit: bool = True):
     """out[m,n] = epilogue(sum_s A_s[m,:] . B_s[n,:]); A_s logical (M,K_s), B_s logical (N,K_s).
-    tc=True (every B_s is a weight): offer the pre-split weights so the library may take the tcgen05 path."""
+    tc=True: offer the tcgen05 path. presplit=True (every B_s is a weight): hand over the cached hi/lo split of the
+    weights; presplit=False (B_s are activations, e.g. weight gradients): the kernel splits both operands itself."""
     lib = _lib.load()
     M, N = out.shape
     d = GemmDesc()
@@ -149,19 +150,25 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
     if split_k is None:
         tiles = ((M + 127) // 128) * ((N + 63) // 64)
         split_k = 1
-        if not want_tc and tiles < _SM_COUNT and ktiles >= 16:
+        if want_tc and not presplit:
+            # activation x activation on the tensor cores: (128 x <=160) tiles, k blocks of 32, one CTA per work item
+            tc_tiles = ((M + 127) // 128) * ((N + 159) // 160)
+            if tc_tiles < _SM_COUNT:
+                split_k = max(1, min(_SM_COUNT // tc_tiles, ktiles // 16))
+        elif not want_tc and tiles < _SM_COUNT and ktiles >= 16:
             split_k = max(1, min(ktiles // 8, (2 * _SM_COUNT + tiles - 1) // tiles))
     ws = None
     if split_k > 1:
         ws = torch.empty((split_k * M * N,), dtype=torch.float32, device=out.device)
         d.workspace = ws.data_ptr()
     d.split_k = split_k
-    if want_tc and split_k <= 1:
-        keep_alive = []
-        for s, (a, b) in enumerate(segments):
-            hi, lo = split_weight(b)
-            keep_alive.append((hi, lo))
-            d.B_hi[s], d.B_lo[s], d.ld_split[s] = hi.data_ptr(), lo.data_ptr(), hi.stride(0)
+    if want_tc and (split_k <= 1 or not presplit):
+        if presplit:
+            keep_alive = []
+            for s, (a, b) in enumerate(segments):
+                hi, lo = split_weight(b)
+                keep_alive.append((hi, lo))
+                d.B_hi[s], d.B_lo[s], d.ld_split[s] = hi.data_ptr(), lo.data_ptr(), hi.stride(0)
         d.tc_mode, d.tc_n_tiles = 1, tc_n_tiles
     if DEBUG_TC_REPORT:
         global LAST_GEMM_USED_TC
@@ -324,7 +331,7 @@ class GGNNLayerFn(torch.autograd.Function):
 
         def wgrad(dg, act):
             w = torch.empty((H, H), **f32)
-            gemm([(dg.t(), act.t())], w)
+            gemm([(dg.t(), act.t())], w, tc=True, presplit=False)
             return w
 
         # order of inputs: ... 8:Wp 9:Wz0 10:bz0 11:Wz1 12:bz1 13:Wr0 14:br0 15:Wr1 16:br1 17:Wh0 18:bh0 19:Wh1 20:bh1
@@ -351,7 +358,7 @@ class GGNNLayerFn(torch.autograd.Function):
             # dWp^T (Din,H) = Xd^T @ dx  (gather + dropout are applied on the A operand)
             wT = torch.empty((Din, H), **f32)
             if feat is not None:
-                gemm([(_rows2d(feat).t(), dx.t())], wT, **drop)
+                gemm([(_rows2d(feat).t(), dx.t())], wT, tc=True, presplit=False, **drop)
             else:
                 a_view = Raw(table.data_ptr(), table.stride(0), 0, (M, Din))
                 gemm([(a_view.t(), dx.t())], wT, rowidx=rowidx, **drop)
@@ -435,7 +442,7 @@ class ConcatAttFn(torch.autograd.Function):
             gemm([(de.t(), t.t())], dW2)
         if need[3]:
             dW1 = torch.empty((H, X + Dr), **f32)
-            gemm([(du.t(), right2d.t())], dW1[:, X:])
+            gemm([(du.t(), right2d.t())], dW1[:, X:], tc=True, presplit=False)
             if left is not None:
                 gemm([(du_sum.t(), left.contiguous().t())], dW1[:, :X])
         if left is not None and need[0]:

@@ -90,12 +90,17 @@ typedef struct get_gemm_desc {
    * order by a second kernel (deterministic), then the epilogue is applied. */
   int32_t split_k; int32_t _pad1;
   float* workspace;
-  /* Tensor-core path (tcgen05, 3xTF32 error-compensated: fp32-level accuracy). Used when tc_mode == 1 and the
-   * descriptor is eligible: every A segment contiguous along k (trans == 0, ld % 4 == 0, K % 4 == 0, K >= 32),
-   * no split-K, and every B segment ALSO given pre-split as two k-contiguous (N, K[s]) row-major matrices
-   * B_hi[s] (tf32-rounded) and B_lo[s] (= B - B_hi) with leading dimension ld_split[s] (see
-   * get_split_tf32_f32; a transposed B is simply split into a k-contiguous copy). B[s] stays the original
-   * operand: ineligible descriptors fall back to the exact SIMT path. tc_n_tiles: CTA tiles along N (0 = auto). */
+  /* Tensor-core path (tcgen05, 3xTF32 error-compensated: fp32-level accuracy), offered when tc_mode == 1; the library
+   * takes it when the descriptor is eligible and otherwise falls back to the exact SIMT path:
+   *  (a) persistent TMA-fed kernel: every A segment 16-byte aligned with ld % 4 == 0, no row gather, no A dropout, all
+   *      segments with the same `trans`; B either given pre-split (below) or raw with the same `trans` in all segments.
+   *      Operands with trans == 1 (both activations: weight gradients) are consumed MN-major, no transposition pass.
+   *      split_k > 1 is honoured (k blocks of 32) through `workspace`.
+   *  (b) register-staged kernel for gathered / dropped-out A operands: A contiguous along k (trans == 0, ld % 4 == 0,
+   *      K % 4 == 0, K >= 32), no split-K, B pre-split.
+   * Pre-split B: two k-contiguous (N, K[s]) row-major matrices B_hi[s] (tf32-rounded) and B_lo[s] (= B - B_hi) with
+   * leading dimension ld_split[s] (see get_split_tf32_f32; a transposed B is simply split into a k-contiguous copy).
+   * B[s] stays the original operand for the fallback. tc_n_tiles: CTA tiles along N (0 = auto). */
   const float* B_hi[GET_GEMM_MAX_SEG];
   const float* B_lo[GET_GEMM_MAX_SEG];
   int64_t ld_split[GET_GEMM_MAX_SEG];
@@ -104,7 +109,8 @@ typedef struct get_gemm_desc {
 
 int get_gemm_f32(const get_gemm_desc* desc, void* stream);
 
-/* 1 if the descriptor would run on the tcgen05 path, 0 if on the SIMT path, <0 on invalid descriptors. */
+/* 2 / 1 if the descriptor would run on the tcgen05 path (persistent TMA-fed / register-staged kernel), 0 if on the
+ * SIMT path, <0 on invalid descriptors. */
 int get_gemm_f32_uses_tc(const get_gemm_desc* desc);
 
 /* Error-compensated TF32 split of a weight matrix for the tensor-core path:

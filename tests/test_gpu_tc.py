@@ -29,7 +29,7 @@ def test_tc_gemm_plain(M, N, K, nt):
     ref = a.double() @ b.double().t() + bias.double()
     out = torch.empty(M, N, device=DEV)
     ops.gemm([(a.to(DEV), b.to(DEV))], out, bias0=bias.to(DEV), tc=True, tc_n_tiles=nt)
-    assert ops.LAST_GEMM_USED_TC == 1
+    assert ops.LAST_GEMM_USED_TC in (1, 2)
     mag = float((a.double().abs() @ b.double().abs().t()).max())
     # the tensor core accumulates in fp32 without round-to-nearest: allow the bound to grow with the contraction length
     _check(out, ref, mag, "plain", scale=max(1.0, K / 512.0))
@@ -49,7 +49,7 @@ def test_tc_gemm_segments_transposed_weights_accumulate_epilogues():
     r, out1 = torch.empty(M, H, device=DEV), torch.empty(M, H, device=DEV)
     ops.gemm([(ad, w0d), (xd, w1d)], r, epilogue=L.EPI_SIGMOID, bias0=b0.to(DEV), bias1=b1.to(DEV), aux0=xd, out1=out1,
              tc=True)
-    assert ops.LAST_GEMM_USED_TC == 1
+    assert ops.LAST_GEMM_USED_TC in (1, 2)
     v = a.double() @ w0.double().t() + x.double() @ w1.double().t() + b0.double() + b1.double()
     assert float((r.cpu().double() - torch.sigmoid(v)).abs().max()) < 8e-6
     assert float((out1.cpu().double() - torch.sigmoid(v) * x.double()).abs().max()) < 5e-6
@@ -58,7 +58,7 @@ def test_tc_gemm_segments_transposed_weights_accumulate_epilogues():
     o, hh = torch.empty(M, H, device=DEV), torch.empty(M, H, device=DEV)
     ops.gemm([(ad, w0d), (rxd, w2d)], o, epilogue=L.EPI_TANH_BLEND, bias0=b0.to(DEV), bias1=b1.to(DEV), aux0=z.to(DEV),
              aux1=xd, out1=hh, tc=True)
-    assert ops.LAST_GEMM_USED_TC == 1
+    assert ops.LAST_GEMM_USED_TC in (1, 2)
     v = a.double() @ w0.double().t() + rx.double() @ w2.double().t() + b0.double() + b1.double()
     assert float((hh.cpu().double() - torch.tanh(v)).abs().max()) < 2e-5
     assert float((o.cpu().double() - (torch.tanh(v) * z.double() + x.double() * (1 - z.double()))).abs().max()) < 2e-5
@@ -66,7 +66,7 @@ def test_tc_gemm_segments_transposed_weights_accumulate_epilogues():
     c0 = _rand(M, H, seed=10)
     c = c0.clone().to(DEV)
     ops.gemm([(ad, w0d.t()), (xd, w1d.t()), (rxd, w2d.t())], c, accumulate=True, tc=True)
-    assert ops.LAST_GEMM_USED_TC == 1
+    assert ops.LAST_GEMM_USED_TC in (1, 2)
     ref = c0.double() + a.double() @ w0.double() + x.double() @ w1.double() + rx.double() @ w2.double()
     mag = float((a.double().abs() @ w0.double().abs()).max()) * 3
     _check(c, ref, mag, "3-seg accumulate")
@@ -76,7 +76,7 @@ def test_tc_gemm_segments_transposed_weights_accumulate_epilogues():
     lp = _rand(G, H, seed=12).to(DEV)
     t = torch.empty(M, H, device=DEV)
     ops.gemm([(ad, w1cat[:, H:])], t, epilogue=L.EPI_TANH_ROWGROUP, aux0=lp, group_rows=P, tc=True)
-    assert ops.LAST_GEMM_USED_TC == 1
+    assert ops.LAST_GEMM_USED_TC in (1, 2)
     ref = torch.tanh(a.double() @ w1cat[:, H:].cpu().double().t() + lp.cpu().double().repeat_interleave(P, 0))
     assert float((t.cpu().double() - ref).abs().max()) < 1e-5
     ops.DEBUG_TC_REPORT = False
@@ -95,14 +95,14 @@ def test_tc_gemm_gather_dropout_and_weight_refresh():
     out = torch.empty(M, N, device=DEV)
     ops.gemm([(ops.Raw(td.data_ptr(), K, 0, (M, K)), wd)], out, rowidx=ids.to(DEV), drop_p=p, drop_seed=seed,
              drop_cols=K, tc=True)
-    assert ops.LAST_GEMM_USED_TC == 1
+    assert ops.LAST_GEMM_USED_TC in (1, 2)
     ref = (table[ids].double() * mask.double()) @ w.double().t()
     _check(out, ref, float(((table[ids].abs().double() * 1.25) @ w.double().abs().t()).max()), "gather+dropout")
     # dX through dropout (epilogue mask) with a transposed weight
     dx = _rand(M, N, seed=4, scale=0.1).to(DEV)
     o2 = torch.empty(M, K, device=DEV)
     ops.gemm([(dx, wd.t())], o2, epilogue=L.EPI_DROPOUT_OUT, drop_out_p=p, drop_out_seed=seed, tc=True)
-    assert ops.LAST_GEMM_USED_TC == 1
+    assert ops.LAST_GEMM_USED_TC in (1, 2)
     ref = (dx.cpu().double() @ w.double()) * mask.double()
     assert float((o2.cpu().double() - ref).abs().max()) < 5e-6
     # in-place weight update (optimizer step) must refresh the cached split
@@ -142,3 +142,38 @@ def test_tc_and_simt_paths_agree_on_model_gradients():
     assert float((res[True][0] - res[False][0]).abs().max()) < 1e-5
     for n, g in res[True][1].items():
         assert float((g - res[False][1][n]).abs().max()) < 1e-5, n
+
+
+@pytest.mark.parametrize("Mo,No,K,split", [(300, 300, 21600, None), (300, 1628, 960, None), (300, 300, 1000, 1), (152, 96, 520, 3),
+                                           (512, 512, 4100, None)])
+def test_tc2_weight_gradient_mn_major_splitk(Mo, No, K, split):
+    """dW (Mo,No) = dG^T (Mo,K) @ X (K,No): both operands are (K, .) row-major activations, consumed MN-major by the
+    persistent tcgen05 kernel (in-kernel hi/lo split of both operands, deterministic split-K)."""
+    from get_b200 import ops
+    ops.DEBUG_TC_REPORT = True
+    dg, x = _rand(K, Mo, seed=21, scale=0.3), _rand(K, No, seed=22, scale=0.5)
+    ref = dg.double().t() @ x.double()
+    w = torch.empty(Mo, No, device=DEV)
+    ops.gemm([(dg.to(DEV).t(), x.to(DEV).t())], w, tc=True, presplit=False, split_k=split)
+    assert ops.LAST_GEMM_USED_TC == 2
+    mag = float((dg.double().abs().t() @ x.double().abs()).max())
+    _check(w, ref, mag, "wgrad", scale=1.0)
+    w2 = torch.empty(Mo, No, device=DEV)
+    ops.gemm([(dg.to(DEV).t(), x.to(DEV).t())], w2, tc=True, presplit=False, split_k=split)
+    assert torch.equal(w, w2), "split-K reduction must be deterministic"
+    ops.DEBUG_TC_REPORT = False
+
+
+def test_tc2_is_the_path_for_plain_weight_gemms_and_handles_tails():
+    from get_b200 import _lib as L
+    from get_b200 import ops
+    ops.DEBUG_TC_REPORT = True
+    for (M, N, K) in [(21600, 300, 300), (129, 24, 40), (1000, 300, 52), (4097, 512, 512)]:
+        a, b, bias = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
+        out = torch.empty(M, N, device=DEV)
+        ops.gemm([(a.to(DEV), b.to(DEV))], out, bias0=bias.to(DEV), tc=True)
+        assert ops.LAST_GEMM_USED_TC == 2, (M, N, K)
+        ref = a.double() @ b.double().t() + bias.double()
+        mag = float((a.double().abs() @ b.double().abs().t()).max())
+        _check(out, ref, mag, "tc2 plain %s" % ((M, N, K),))
+    ops.DEBUG_TC_REPORT = False
