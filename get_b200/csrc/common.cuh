@@ -68,6 +68,12 @@ __device__ __forceinline__ void drop_apply4(uint32_t seed, uint64_t idx4, uint32
 
 // ---- math -------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+// Epilogue activations: ex2.approx / rcp.approx based, absolute error ~2e-7 on outputs in [-1, 1] (fp32 round-off level)
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_fast(float v) {
+  const float c = fminf(fmaxf(v, -15.0f), 15.0f);
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * c));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

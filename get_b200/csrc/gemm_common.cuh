@@ -57,10 +57,46 @@ __device__ __forceinline__ void store4(float* base, bool vec, int nvalid, const 
   }
 }
 
-__device__ __forceinline__ void epilogue4(const GemmParams& p, int m, int n, float acc[4]) {
-  const int nvalid = min(4, p.N - n);
-  const bool vec = p.vec_epi != 0;  // host guarantees N % 4 == 0 and 16-byte alignment of every pointer used
-  float v[4], b[4];
+// The epilogue is split in two so that callers with several (m, n) quads in flight can issue ALL their global loads
+// before the first dependent use (the loads of one quad must not wait behind the stores of the previous one).
+struct EpiIn {
+  float a0[4], a1[4], o[4];   // aux0 / aux1 / previous C (accumulate) or out1 (DGATE_R)
+};
+
+// EPI >= 0: epilogue kind known at compile time (specialised kernels: no switch, small code); EPI < 0: p.epilogue
+template <int EPI, bool VEC = false>
+__device__ __forceinline__ void epilogue4_load_t(const GemmParams& p, int m, int n, EpiIn& in) {
+  const int nvalid = VEC ? 4 : min(4, p.N - n);
+  const bool vec = VEC || p.vec_epi != 0;
+  switch (EPI >= 0 ? EPI : p.epilogue) {
+    case GET_EPI_STORE:
+    case GET_EPI_DROPOUT_OUT:
+      if (p.accumulate) load4(p.C + (int64_t)m * p.ldc + n, vec, nvalid, in.o);
+      break;
+    case GET_EPI_SIGMOID:
+      if (p.out1) load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, in.a0);
+      break;
+    case GET_EPI_TANH_BLEND:
+      load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, in.a0);  // z
+      load4(p.aux1 + (int64_t)m * p.ld_aux1 + n, vec, nvalid, in.a1);  // x
+      break;
+    case GET_EPI_TANH_ROWGROUP:
+      load4(p.aux0 + (int64_t)(m / p.group_rows) * p.ld_aux0 + n, vec, nvalid, in.a0);
+      break;
+    case GET_EPI_DGATE_R:
+      load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, in.a0);  // x
+      load4(p.aux1 + (int64_t)m * p.ld_aux1 + n, vec, nvalid, in.a1);  // r
+      load4(p.out1 + (int64_t)m * p.ld_out1 + n, vec, nvalid, in.o);
+      break;
+    default: break;
+  }
+}
+
+template <int EPI, bool VEC = false>
+__device__ __forceinline__ void epilogue4_apply_t(const GemmParams& p, int m, int n, const float acc[4], const EpiIn& in) {
+  const int nvalid = VEC ? 4 : min(4, p.N - n);
+  const bool vec = VEC || p.vec_epi != 0;  // host guarantees N % 4 == 0 and 16-byte alignment of every pointer used
+  float v[4], b[4], o[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) v[e] = p.alpha * acc[e];
   if (p.bias0) {
@@ -74,57 +110,47 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, int m, int n, flo
     for (int e = 0; e < 4; ++e) v[e] += b[e];
   }
   float* crow = p.C + (int64_t)m * p.ldc + n;
-  float a0[4], a1[4], o[4];
-  switch (p.epilogue) {
+  switch (EPI >= 0 ? EPI : p.epilogue) {
     case GET_EPI_STORE: {
       if (p.accumulate) {
-        load4(crow, vec, nvalid, o);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] += o[e];
+        for (int e = 0; e < 4; ++e) v[e] += in.o[e];
       }
       store4(crow, vec, nvalid, v);
     } break;
     case GET_EPI_SIGMOID: {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = sigmoidf_(v[e]);
+      for (int e = 0; e < 4; ++e) v[e] = sigmoid_fast(v[e]);
       store4(crow, vec, nvalid, v);
       if (p.out1) {
-        load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, a0);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = v[e] * a0[e];
+        for (int e = 0; e < 4; ++e) o[e] = v[e] * in.a0[e];
         store4(p.out1 + (int64_t)m * p.ld_out1 + n, vec, nvalid, o);
       }
     } break;
     case GET_EPI_TANH_BLEND: {
-      load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, a0);  // z
-      load4(p.aux1 + (int64_t)m * p.ld_aux1 + n, vec, nvalid, a1);  // x
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        v[e] = tanhf(v[e]);
-        o[e] = v[e] * a0[e] + a1[e] * (1.0f - a0[e]);
+        v[e] = tanh_fast(v[e]);
+        o[e] = v[e] * in.a0[e] + in.a1[e] * (1.0f - in.a0[e]);
       }
       if (p.out1) store4(p.out1 + (int64_t)m * p.ld_out1 + n, vec, nvalid, v);
       store4(crow, vec, nvalid, o);
     } break;
     case GET_EPI_TANH_ROWGROUP: {
-      load4(p.aux0 + (int64_t)(m / p.group_rows) * p.ld_aux0 + n, vec, nvalid, a0);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = tanhf(v[e] + a0[e]);
+      for (int e = 0; e < 4; ++e) v[e] = tanh_fast(v[e] + in.a0[e]);
       store4(crow, vec, nvalid, v);
     } break;
     case GET_EPI_DGATE_R: {
-      load4(p.aux0 + (int64_t)m * p.ld_aux0 + n, vec, nvalid, a0);  // x
-      load4(p.aux1 + (int64_t)m * p.ld_aux1 + n, vec, nvalid, a1);  // r
-      float* o1 = p.out1 + (int64_t)m * p.ld_out1 + n;
-      load4(o1, vec, nvalid, o);
       float c[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        c[e] = v[e] * a0[e] * a1[e] * (1.0f - a1[e]);
-        o[e] += v[e] * a1[e];
+        c[e] = v[e] * in.a0[e] * in.a1[e] * (1.0f - in.a1[e]);
+        o[e] = in.o[e] + v[e] * in.a1[e];
       }
       store4(crow, vec, nvalid, c);
-      store4(o1, vec, nvalid, o);
+      store4(p.out1 + (int64_t)m * p.ld_out1 + n, vec, nvalid, o);
     } break;
     case GET_EPI_DROPOUT_OUT: {
 #pragma unroll
@@ -133,19 +159,24 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, int m, int n, flo
         v[e] = keep ? v[e] * p.drop_out_scale : 0.f;
       }
       if (p.accumulate) {
-        load4(crow, vec, nvalid, o);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] += o[e];
+        for (int e = 0; e < 4; ++e) v[e] += in.o[e];
       }
       store4(crow, vec, nvalid, v);
     } break;
     case GET_EPI_TANH: {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = tanhf(v[e]);
+      for (int e = 0; e < 4; ++e) v[e] = tanh_fast(v[e]);
       store4(crow, vec, nvalid, v);
     } break;
     default: break;
   }
+}
+
+__device__ __forceinline__ void epilogue4(const GemmParams& p, int m, int n, float acc[4]) {
+  EpiIn in;
+  epilogue4_load_t<-1>(p, m, n, in);
+  epilogue4_apply_t<-1>(p, m, n, acc, in);
 }
 
 

@@ -10,14 +10,15 @@
 //   * MN-major operands (the weight-gradient contraction dW = dG^T . X, both operands (K,MN) row-major): boxes
 //     {32 mn, 32 k} (TMA swizzle 128B_ATOM_32B), consumed through MN-major UMMA descriptors (SWIZZLE_128B_BASE32B, the
 //     only MN-major layout fp32 operands have) -- no transposition pass anywhere.
-// Warp roles (320 threads, one persistent CTA per SM, static round-robin over work items):
+// Warp roles (448 threads, one persistent CTA per SM, static round-robin over work items):
 //   warp 0      TMA producer                         warp 1      tcgen05.mma issuer, owns the TMEM allocation
 //   warps 2-5   splitter: raw tile -> hi (tf32 round-to-nearest, in place) + lo (second buffer), smem -> smem
-//   warps 6-9   epilogue: tcgen05.ld main+small -> fused epilogue (gemm_common.cuh) -> global; with two TMEM
+//   warps 6-13  epilogue: tcgen05.ld main+small -> fused epilogue (gemm_common.cuh) -> global; with two TMEM
 //               accumulator sets the epilogue of item i overlaps the main loop of item i+1
 // Work item = (m tile, n tile, k split); split-K items store raw partial tiles that gemm_splitk_reduce_kernel sums in
 // a fixed order (deterministic weight gradients).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -29,10 +30,13 @@ namespace getb {
 
 constexpr int T2_BM = 128;
 constexpr int T2_BK = 32;
-constexpr int T2_THREADS = 320;
+constexpr int T2_THREADS = 448;                      // 14 warps: TMA, MMA, 4 splitter, 8 epilogue
+constexpr int T2_EPI_WARPS = 8;
 constexpr int T2_A_TILE = T2_BM * 128;   // bytes of one A tile (hi or lo)
 constexpr int T2_MAX_STAGES = 4;
 constexpr uint32_t T2_SPIN_LIMIT = 1u << 28;
+constexpr int T2_STG_LD = 36;                        // floats per row of the epilogue staging tile (32 + 4: conflict-free)
+constexpr int T2_STG_BYTES = T2_EPI_WARPS * 32 * T2_STG_LD * 4;
 
 struct Tc2Maps {
   CUtensorMap a[GET_GEMM_MAX_SEG];
@@ -48,6 +52,7 @@ struct Tc2Cfg {
   int split_b;           // B arrives raw and is split in the kernel (otherwise B_hi / B_lo are loaded pre-split)
   int ntm, ntn, splits, kb_per_split, items;
   uint32_t b_tile, stage_bytes;
+  int debug;             // perf experiments only (GET_B200_T2_DEBUG): 1 = main MMA only, 2 = splitter skips its work
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -125,6 +130,21 @@ __device__ __forceinline__ uint32_t f32_to_tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
+// explicit shared-space accesses (the 1024-byte realignment of the dynamic buffer hides the address space from nvcc)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// hi = tf32 round-to-nearest of v, lo = tf32 round-to-nearest of the remainder
+__device__ __forceinline__ void split4(const float4& v, uint4& hi, uint4& lo) {
+  hi.x = f32_to_tf32_rn(v.x); hi.y = f32_to_tf32_rn(v.y); hi.z = f32_to_tf32_rn(v.z); hi.w = f32_to_tf32_rn(v.w);
+  lo.x = f32_to_tf32_rn(v.x - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rn(v.y - __uint_as_float(hi.y));
+  lo.z = f32_to_tf32_rn(v.z - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rn(v.w - __uint_as_float(hi.w));
+}
 }  // namespace t2
 
 // locate k-block `kb` (global index over the segments): segment and k offset inside it
@@ -134,6 +154,7 @@ __device__ __forceinline__ void t2_locate(const Tc2Cfg& cfg, int nseg, int kb, i
   kin = kb * T2_BK;
 }
 
+template <int EPI>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc2Cfg cfg, const __grid_constant__ Tc2Maps maps) {
   using namespace t2;
@@ -142,8 +163,11 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
   __shared__ __align__(8) uint64_t bar_ready[T2_MAX_STAGES];   // hi/lo tiles complete (128 splitter arrivals)
   __shared__ __align__(8) uint64_t bar_empty[T2_MAX_STAGES];   // MMAs that read the stage retired (tcgen05.commit)
   __shared__ __align__(8) uint64_t bar_accf[2];                // accumulator set complete (tcgen05.commit)
-  __shared__ __align__(8) uint64_t bar_acce[2];                // accumulator set drained (128 epilogue arrivals)
+  __shared__ __align__(8) uint64_t bar_acce[2];                // accumulator set drained (all epilogue threads arrive)
   __shared__ uint32_t tmem_holder;
+  __shared__ long long dbg_ts[4][24];   // GET_B200_T2_DEBUG=9: per-role timeline of CTA 0
+  const long long dbg_t0 = clock64();
+#define T2_DBG(role, idx) do { if (cfg.debug == 9 && blockIdx.x == 0 && (idx) < 24) dbg_ts[role][idx] = clock64() - dbg_t0; } while (0)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = cfg.BN;
@@ -158,7 +182,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_accf[b], 1);
-      mbar_init(&bar_acce[b], 128);
+      mbar_init(&bar_acce[b], 32 * T2_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -191,6 +215,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           int seg, kin;
           t2_locate(cfg, p.nseg, kb, seg, kin);
           mbar_wait(&bar_empty[stage], phase ^ 1);
+          if (kb == kb0) T2_DBG(0, it * 2); if (kb == kb1 - 1) T2_DBG(0, it * 2 + 1);
           const uint32_t sa = smem_base + (uint32_t)stage * cfg.stage_bytes;
           const uint32_t sbh = sa + 2u * T2_A_TILE, sbl = sbh + cfg.b_tile;
           mbar_arrive_expect_tx(&bar_raw[stage], tx);
@@ -230,12 +255,14 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
         const int kb0 = z * cfg.kb_per_split, kb1 = min(cfg.kblocks_total, kb0 + cfg.kb_per_split);
         mbar_wait(&bar_acce[acc], acc_phase ^ 1);
         tc_fence_after();
+        T2_DBG(1, it * 3);
         const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * BN);
         const uint32_t d_small = d_main + (uint32_t)BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bar_raw[stage], phase);
           mbar_wait(&bar_ready[stage], phase);
           tc_fence_after();
+          if (kb == kb0) T2_DBG(1, it * 3 + 1);
           const uint32_t a_hi = smem_base + (uint32_t)stage * cfg.stage_bytes;
           const uint32_t a_lo = a_hi + T2_A_TILE;
           const uint32_t b_hi = a_lo + T2_A_TILE;
@@ -245,14 +272,18 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
             const uint64_t dah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t dbh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt), dbl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
             const uint32_t first = (kb > kb0 || ks > 0) ? 1u : 0u;
+            if (cfg.debug == 3 && !(kb + 1 == kb1 && ks == 0)) continue;   // experiment: (almost) no MMAs
             umma_tf32(d_main, dah, dbh, idesc, first);
-            umma_tf32(d_small, dah, dbl, idesc, first);
-            umma_tf32(d_small, dal, dbh, idesc, 1u);
+            if (cfg.debug != 1 && cfg.debug != 3) {
+              umma_tf32(d_small, dah, dbl, idesc, first);
+              umma_tf32(d_small, dal, dbh, idesc, 1u);
+            }
           }
           umma_commit(&bar_empty[stage]);
           if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_accf[acc]);
+        T2_DBG(1, it * 3 + 2);
         if (cfg.acc_bufs == 2) {
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -267,7 +298,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
     const int t = tid - 64;   // 0..127
     int stage = 0;
     uint32_t phase = 0;
-    const int a_chunks = T2_A_TILE / 16 / 128;                       // 16-byte chunks per thread in the A tile
+    constexpr int a_chunks = T2_A_TILE / 16 / 128;                   // 16-byte chunks per thread in the A tile
     const int b_chunks = cfg.split_b ? (int)(cfg.b_tile / 16) : 0;   // total chunks of the B tile
     for (int it = 0; it < n_my; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
@@ -275,31 +306,32 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
       const int kb0 = z * cfg.kb_per_split, kb1 = min(cfg.kblocks_total, kb0 + cfg.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&bar_raw[stage], phase);
-        uint8_t* a_hi = smem + (size_t)stage * cfg.stage_bytes;
-        uint8_t* a_lo = a_hi + T2_A_TILE;
+        if (t == 0 && kb == kb0) T2_DBG(3, it * 2); if (t == 0 && kb == kb1 - 1) T2_DBG(3, it * 2 + 1);
+        const uint32_t a_hi = smem_base + (uint32_t)stage * cfg.stage_bytes;
+        const uint32_t a_lo = a_hi + T2_A_TILE;
+        if (cfg.debug != 2 && cfg.debug != 3) {
+          float4 v[a_chunks];
 #pragma unroll
-        for (int i = 0; i < a_chunks; ++i) {
-          const uint32_t off = (uint32_t)(t + i * 128) * 16u;
-          const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
-          uint4 hi, lo;
-          hi.x = f32_to_tf32_rn(v.x); hi.y = f32_to_tf32_rn(v.y); hi.z = f32_to_tf32_rn(v.z); hi.w = f32_to_tf32_rn(v.w);
-          lo.x = f32_to_tf32_rn(v.x - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rn(v.y - __uint_as_float(hi.y));
-          lo.z = f32_to_tf32_rn(v.z - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rn(v.w - __uint_as_float(hi.w));
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+          for (int i = 0; i < a_chunks; ++i) v[i] = lds128(a_hi + (uint32_t)(t + i * 128) * 16u);
+#pragma unroll
+          for (int i = 0; i < a_chunks; ++i) {
+            const uint32_t off = (uint32_t)(t + i * 128) * 16u;
+            uint4 hi, lo;
+            split4(v[i], hi, lo);
+            sts128(a_hi + off, hi);
+            sts128(a_lo + off, lo);
+          }
         }
         if (cfg.split_b) {
-          uint8_t* b_hi = a_lo + T2_A_TILE;
-          uint8_t* b_lo = b_hi + cfg.b_tile;
+          const uint32_t b_hi = a_lo + T2_A_TILE;
+          const uint32_t b_lo = b_hi + cfg.b_tile;
           for (int c = t; c < b_chunks; c += 128) {
             const uint32_t off = (uint32_t)c * 16u;
-            const float4 v = *reinterpret_cast<const float4*>(b_hi + off);
+            const float4 v = lds128(b_hi + off);
             uint4 hi, lo;
-            hi.x = f32_to_tf32_rn(v.x); hi.y = f32_to_tf32_rn(v.y); hi.z = f32_to_tf32_rn(v.z); hi.w = f32_to_tf32_rn(v.w);
-            lo.x = f32_to_tf32_rn(v.x - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rn(v.y - __uint_as_float(hi.y));
-            lo.z = f32_to_tf32_rn(v.z - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rn(v.w - __uint_as_float(hi.w));
-            *reinterpret_cast<uint4*>(b_hi + off) = hi;
-            *reinterpret_cast<uint4*>(b_lo + off) = lo;
+            split4(v, hi, lo);
+            sts128(b_hi + off, hi);
+            sts128(b_lo + off, lo);
           }
         }
         fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -309,42 +341,104 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
     }
   } else {
     // =========================================== epilogue ===============================================
+    // TMEM hands every thread one output ROW; a per-warp 32 x 32 staging tile in shared memory turns that into 8 lanes
+    // per row x 4 rows per instruction, so every global access of the fused epilogue is a full 128-byte line.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int chalf = (warp - 6) >> 2;            // two warps per quarter: even / odd 32-column chunks
+    const uint32_t stg = smem_base + (uint32_t)cfg.stages * cfg.stage_bytes + (uint32_t)(warp - 6) * (32u * T2_STG_LD * 4u);
+    const int rrow = lane >> 3, rq = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int it = 0; it < n_my; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
       const int nt = item % cfg.ntn, mt = (item / cfg.ntn) % cfg.ntm, z = item / (cfg.ntn * cfg.ntm);
-      const int m = mt * T2_BM + quarter * 32 + lane;
+      const int m_base = mt * T2_BM + quarter * 32;
       const int n0 = nt * BN;
       mbar_wait(&bar_accf[acc], acc_phase);
       tc_fence_after();
+      if (warp == 6 && lane == 0) T2_DBG(2, it * 2);
       const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN);
       const uint32_t t_small = t_main + (uint32_t)BN;
-      for (int col = 0; col < BN; col += 16) {
-        uint32_t rm[16], rs[16];
+      const int nch = (BN + 31) / 32;     // 32-column chunks; this warp takes chunks chalf, chalf + 2, ...
+      const int last_col = (nch - 1 >= chalf) ? ((nch - 1 - chalf) / 2 * 2 + chalf) * 32 : -1;
+      if (last_col < 0) {                 // single-chunk tiles: the odd warps have nothing to read
+        tc_fence_before();
+        mbar_arrive(&bar_acce[acc]);
+      }
+      for (int col = chalf * 32; col < BN; col += 64) {
+        const bool two = col + 16 < BN;
+        uint32_t rm[16], rs[16], rm2[16], rs2[16];
         tmem_ld16_nowait(t_main + (uint32_t)col, rm);
         tmem_ld16_nowait(t_small + (uint32_t)col, rs);
+        if (two) {
+          tmem_ld16_nowait(t_main + (uint32_t)col + 16u, rm2);
+          tmem_ld16_nowait(t_small + (uint32_t)col + 16u, rs2);
+        }
         tmem_ld_wait();
-        if (m < p.M) {
+        if (col == last_col) {           // last chunk of this accumulator set for this warp: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&bar_acce[acc]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = __float_as_uint(__uint_as_float(rm[q * 4 + 0]) + __uint_as_float(rs[q * 4 + 0]));
+          v.y = __float_as_uint(__uint_as_float(rm[q * 4 + 1]) + __uint_as_float(rs[q * 4 + 1]));
+          v.z = __float_as_uint(__uint_as_float(rm[q * 4 + 2]) + __uint_as_float(rs[q * 4 + 2]));
+          v.w = __float_as_uint(__uint_as_float(rm[q * 4 + 3]) + __uint_as_float(rs[q * 4 + 3]));
+          sts128(stg + (uint32_t)(lane * T2_STG_LD + q * 4) * 4u, v);
+        }
+        if (two) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int n = n0 + col + q * 4;
-            if (n < p.N) {
-              float v[4];
+            uint4 v;
+            v.x = __float_as_uint(__uint_as_float(rm2[q * 4 + 0]) + __uint_as_float(rs2[q * 4 + 0]));
+            v.y = __float_as_uint(__uint_as_float(rm2[q * 4 + 1]) + __uint_as_float(rs2[q * 4 + 1]));
+            v.z = __float_as_uint(__uint_as_float(rm2[q * 4 + 2]) + __uint_as_float(rs2[q * 4 + 2]));
+            v.w = __float_as_uint(__uint_as_float(rm2[q * 4 + 3]) + __uint_as_float(rs2[q * 4 + 3]));
+            sts128(stg + (uint32_t)(lane * T2_STG_LD + 16 + q * 4) * 4u, v);
+          }
+        }
+        __syncwarp();
+        const int n = n0 + col + rq * 4;
+        if (cfg.debug == 4) continue;    // experiment: no global epilogue traffic
+        if ((two || rq < 4) && n < p.N) {
+          if (cfg.splits > 1) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(rm[q * 4 + e]) + __uint_as_float(rs[q * 4 + e]);
-              if (cfg.splits > 1) {
-                store4(p.workspace + ((int64_t)z * p.M + m) * p.N + n, (p.N & 3) == 0, min(4, p.N - n), v);
-              } else {
-                epilogue4(p, m, n, v);
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + rrow;
+              const int m = m_base + row;
+              if (m < p.M) {
+                const float4 f = lds128(stg + (uint32_t)(row * T2_STG_LD + rq * 4) * 4u);
+                const float v[4] = {f.x, f.y, f.z, f.w};
+                store4(p.workspace + ((int64_t)z * p.M + m) * p.N + n, true, 4, v);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {          // two batches of four rows: all loads first, then math + stores
+              EpiIn in[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int m = m_base + (h * 4 + i) * 4 + rrow;
+                if (m < p.M) epilogue4_load_t<EPI, true>(p, m, n, in[i]);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int row = (h * 4 + i) * 4 + rrow;
+                const int m = m_base + row;
+                if (m < p.M) {
+                  const float4 f = lds128(stg + (uint32_t)(row * T2_STG_LD + rq * 4) * 4u);
+                  const float v[4] = {f.x, f.y, f.z, f.w};
+                  epilogue4_apply_t<EPI, true>(p, m, n, v, in[i]);
+                }
               }
             }
           }
         }
+        __syncwarp();
       }
-      tc_fence_before();
-      mbar_arrive(&bar_acce[acc]);
+      if (warp == 6 && lane == 0) T2_DBG(2, it * 2 + 1);
       if (cfg.acc_bufs == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -355,6 +449,13 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
   }
   tc_fence_before();
   __syncthreads();
+  if (cfg.debug == 9 && blockIdx.x == 0 && tid == 0) {
+    for (int it = 0; it < n_my && it < 4; ++it)
+      printf("T2DBG it=%d prod[%lld %lld] split[%lld %lld] mma[acce %lld ready %lld commit %lld] epi[%lld %lld]\n", it,
+             dbg_ts[0][it * 2], dbg_ts[0][it * 2 + 1], dbg_ts[3][it * 2], dbg_ts[3][it * 2 + 1], dbg_ts[1][it * 3], dbg_ts[1][it * 3 + 1],
+             dbg_ts[1][it * 3 + 2], dbg_ts[2][it * 2], dbg_ts[2][it * 2 + 1]);
+    printf("T2DBG end %lld\n", clock64() - dbg_t0);
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg.tmem_cols) : "memory");
@@ -440,6 +541,7 @@ static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
   if (d->tc_mode < 1) return 1;
   if (p.M < 1 || p.N < 8) return 1;
   if (p.drop_thr) return 1;                                   // A-operand dropout: register-staged kernel (gemm_tc.cu)
+  if (!p.vec_epi || (p.N & 3)) return 1;                      // the epilogue works on aligned float4 quads only
   memset(&cfg, 0, sizeof(cfg));
   const bool presplit = d->B_hi[0] != nullptr;
   cfg.a_mn = p.A[0].trans;
@@ -483,7 +585,7 @@ static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
   if (best_nt == 0) return 1;
   if (d->tc_n_tiles > 0) {
     const int bn = t2_pad((p.N + d->tc_n_tiles - 1) / d->tc_n_tiles, q);
-    if (bn <= 128 && bn >= 16 && (d->tc_n_tiles - 1) * bn < p.N) best_nt = d->tc_n_tiles;
+    if (bn <= 256 && bn >= 16 && (d->tc_n_tiles - 1) * bn < p.N) best_nt = d->tc_n_tiles;
   }
   cfg.ntn = best_nt;
   cfg.BN = t2_pad((p.N + best_nt - 1) / best_nt, q);
@@ -495,10 +597,16 @@ static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
   cfg.tmem_cols = tc;
   cfg.b_tile = (uint32_t)cfg.BN * 128u;
   cfg.stage_bytes = 2u * T2_A_TILE + 2u * cfg.b_tile;
-  int stages = (224 * 1024 - 2048) / (int)cfg.stage_bytes;
+  int stages = (224 * 1024 - 2048 - T2_STG_BYTES) / (int)cfg.stage_bytes;
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
   if (stages < 2) return 1;
   cfg.stages = stages;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("GET_B200_T2_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  cfg.debug = dbg;
   return 0;
 }
 
@@ -522,15 +630,21 @@ int gemm_tc2_launch(const get_gemm_desc* d, GemmParams& p, cudaStream_t st) {
       if (!t2_make_map(&maps.bh[s], p.B[s].ptr, p.K[s], p.N, p.B[s].ld, T2_BK, cfg.BN, 0)) return 1;
     }
   }
-  const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + 1024;
-  static int max_dyn = -1;
-  if (max_dyn < 0) {
+  const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + T2_STG_BYTES + 1024;
+  typedef void (*KernelFn)(const GemmParams, const Tc2Cfg, const Tc2Maps);
+  static const KernelFn kernels[7] = {gemm_tc2_kernel<0>, gemm_tc2_kernel<1>, gemm_tc2_kernel<2>, gemm_tc2_kernel<3>,
+                                      gemm_tc2_kernel<4>, gemm_tc2_kernel<5>, gemm_tc2_kernel<6>};
+  const int epi = cfg.splits > 1 ? 0 : p.epilogue;
+  if (epi < 0 || epi > 6) return 1;
+  KernelFn fn = kernels[epi];
+  static int max_dyn[7] = {-1, -1, -1, -1, -1, -1, -1};
+  if (max_dyn[epi] < 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tc2_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&fa, fn);
     if (e == cudaSuccess) {
       const int want = 227 * 1024 - (int)((fa.sharedSizeBytes + 1023) / 1024 * 1024);
-      e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-      if (e == cudaSuccess) max_dyn = want;
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      if (e == cudaSuccess) max_dyn[epi] = want;
     }
     if (e != cudaSuccess) {
       set_error("gemm_tc2_kernel: cannot opt in to large shared memory: %s", cudaGetErrorString(e));
@@ -538,9 +652,9 @@ int gemm_tc2_launch(const get_gemm_desc* d, GemmParams& p, cudaStream_t st) {
       return -(int)e - 1000;
     }
   }
-  if ((int)smem > max_dyn) return 1;
+  if ((int)smem > max_dyn[epi]) return 1;
   const int grid = cfg.items < 148 ? cfg.items : 148;
-  gemm_tc2_kernel<<<grid, T2_THREADS, smem, st>>>(p, cfg, maps);
+  fn<<<grid, T2_THREADS, smem, st>>>(p, cfg, maps);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("gemm_tc2_kernel: launch failed: %s", cudaGetErrorString(e));

@@ -101,11 +101,18 @@ def bench_gemm(a):
                                                bias0=b0, bias1=b1, aux0=aux[i], out1=out1[i], tc=True), nsets, a.iters)
         res["sigmoid_tc%d" % tc] = {"ms": med, "TFLOPs_fp32": flops / med / 1e9}
     ops.TC_ENABLED = True
+    for nt in (2, 3, 4, 5):
+        med, best = time_fn(lambda i: ops.gemm([(As[i][s], Ws[s]) for s in range(a.seg)], outs[i], tc=True, tc_n_tiles=nt),
+                            nsets, a.iters)
+        res["store_nt%d" % nt] = {"ms": med, "TFLOPs_fp32": flops / med / 1e9}
+    med, best = time_fn(lambda i: ops.gemm([(As[i][s], Ws[s]) for s in range(a.seg)], outs[i], tc=True, presplit=False, split_k=1),
+                        nsets, a.iters)
+    res["store_rawB"] = {"ms": med, "TFLOPs_fp32": flops / med / 1e9}
     # weight-gradient shape: (N x N) = dg^T (N x M) @ act (M x N)
     dg = [torch.randn(M, N, device=dev) for _ in range(nsets)]
     act = [torch.randn(M, N, device=dev) for _ in range(nsets)]
     w = torch.empty(N, N, device=dev)
-    med, best = time_fn(lambda i: ops.gemm([(dg[i].t(), act[i].t())], w), nsets, a.iters)
+    med, best = time_fn(lambda i: ops.gemm([(dg[i].t(), act[i].t())], w, tc=True, presplit=False), nsets, a.iters)
     res["wgrad"] = {"ms": med, "TFLOPs_fp32": 2.0 * M * N * N / med / 1e9}
     print(json.dumps({"kernel": "gemm", "M": M, "N": N, "K": K, "seg": a.seg, "nsets": nsets, **res}))
 
