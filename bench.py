@@ -247,6 +247,7 @@ def run_ours(args):
         step(resident[b])
         pairs += batches[b]["pairs"]
     e1.record()
+    t_enqueue = time.perf_counter() - t_wall0      # host time to enqueue the K steps (no sync inside)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - launches0
@@ -304,7 +305,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(w, {"parallelism": "dp%d" % world, "mean_pairs_per_step_per_gpu": pairs / args.steps / world,
                                       "grad_allreduce_bytes": reducer.nbytes if world > 1 else 0,
-                                      "wall_s_timed_region": t_wall}),
+                                      "wall_s_timed_region": t_wall,
+                                      "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps}),
             "clocks": clocks,
             "e2e": {"value": pairs_e2e / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},

@@ -48,7 +48,7 @@ SIGNATURES = {
     "get_gsl_mask_adj_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "get_att_pool_fwd_f32": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
     "get_att_pool_bwd_f32": (_I, [_P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _I, _P]),
-    "get_ggnn_gate_bwd_f32": (_I, [_P, _P, _P, _P, _L, _P, _P, _P, _P]),
+    "get_ggnn_gate_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
     "get_colsum_f32": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "get_colsum_workspace_floats": (_L, [_I, _I]),
     "get_rows_gather_f32": (_I, [_P, _L, _P, _I, _I, _P, _L, _P]),
@@ -57,6 +57,10 @@ SIGNATURES = {
     "get_masked_mean_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "get_masked_mean_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "get_dropout_mask_f32": (_I, [_P, _L, _F, _U, _P]),
+    "get_rows_gather_dropout_f32": (_I, [_P, _L, _P, _I, _I, _F, _U, _P, _L, _P]),
+    "get_dropout_salt_set": (_I, [_U, _P]),
+    "get_dropout_salt_advance": (_I, [_P]),
+    "get_dropout_salt_get": (_I, [C.POINTER(C.c_uint32)]),
     "get_cross_entropy_f32": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "get_b200_abi_version": (_I, []),
     "get_b200_last_error": (C.c_char_p, []),
@@ -85,6 +89,8 @@ def load():
         fn.argtypes = args
     if lib.get_b200_abi_version() != 1:
         raise RuntimeError("libget_b200.so ABI version mismatch")
+    # allocate the dropout salt word now (never inside a stream capture); fails harmlessly on a box without a GPU
+    lib.get_dropout_salt_get(C.byref(C.c_uint32(0)))
     _lib = lib
     return lib
 

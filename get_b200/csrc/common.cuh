@@ -11,6 +11,9 @@ namespace getb {
 // ---- status / error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Device word added to every dropout seed (misc.cu). A captured CUDA graph replays the same kernel arguments, so the
+// per-step variation of the masks comes from this word, advanced by a one-thread kernel inside the graph.
+const uint32_t* dropout_salt_ptr();
 
 #define GETB_REQUIRE(cond, ...)                 \
   do {                                          \

@@ -31,6 +31,7 @@ struct GemmParams {
   float drop_scale;
   uint32_t drop_out_thr, drop_out_seed;
   float drop_out_scale;
+  const uint32_t* salt;   // device word added to both dropout seeds
   int split_k, tiles_per_split, tiles_total;
   float* workspace;
   int vec_epi;
@@ -155,7 +156,7 @@ __device__ __forceinline__ void epilogue4_apply_t(const GemmParams& p, int m, in
     case GET_EPI_DROPOUT_OUT: {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        bool keep = drop_keep(p.drop_out_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + e), p.drop_out_thr);
+        bool keep = drop_keep(p.drop_out_seed + __ldg(p.salt), (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + e), p.drop_out_thr);
         v[e] = keep ? v[e] * p.drop_out_scale : 0.f;
       }
       if (p.accumulate) {

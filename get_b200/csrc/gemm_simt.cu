@@ -45,7 +45,7 @@ __device__ __forceinline__ void load_tile(const GemmParams& p, const GemmOp& op,
         if (IS_A && p.drop_thr) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            bool keep = drop_keep(p.drop_seed, (uint64_t)row * (uint64_t)p.drop_cols + (uint64_t)(k + e), p.drop_thr);
+            bool keep = drop_keep(p.drop_seed + __ldg(p.salt), (uint64_t)row * (uint64_t)p.drop_cols + (uint64_t)(k + e), p.drop_thr);
             r[e] = keep ? r[e] * p.drop_scale : 0.f;
           }
         }
@@ -68,7 +68,7 @@ __device__ __forceinline__ void load_tile(const GemmParams& p, const GemmOp& op,
         if (IS_A && p.drop_thr) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            bool keep = drop_keep(p.drop_seed, (uint64_t)k * (uint64_t)p.drop_cols + (uint64_t)(i + e), p.drop_thr);
+            bool keep = drop_keep(p.drop_seed + __ldg(p.salt), (uint64_t)k * (uint64_t)p.drop_cols + (uint64_t)(i + e), p.drop_thr);
             r[e] = keep ? r[e] * p.drop_scale : 0.f;
           }
         }
@@ -262,6 +262,7 @@ int gemm_build_params(const get_gemm_desc* d, GemmParams& p) {
     p.drop_out_thr = drop_threshold(d->drop_out_p);
     p.drop_out_seed = d->drop_out_seed; p.drop_out_scale = 1.0f / (1.0f - d->drop_out_p);
   }
+  p.salt = dropout_salt_ptr();
   p.split_k = d->split_k > 1 ? d->split_k : 1;
   if (p.split_k > tiles) p.split_k = tiles > 0 ? tiles : 1;
   p.tiles_total = tiles;

@@ -206,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TcC
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint64_t base = (uint64_t)(m0 + r0 + 16 * i) * (uint64_t)p.drop_cols + (uint64_t)k;
-          drop_apply4(p.drop_seed, base, p.drop_thr, p.drop_scale, v[i]);
+          drop_apply4(p.drop_seed + __ldg(p.salt), base, p.drop_thr, p.drop_scale, v[i]);
         }
       }
       mbar_wait(&bar_empty[stage], phase ^ 1);

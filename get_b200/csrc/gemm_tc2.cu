@@ -33,7 +33,7 @@ constexpr int T2_BK = 32;
 constexpr int T2_THREADS = 448;                      // 14 warps: TMA, MMA, 4 splitter, 8 epilogue
 constexpr int T2_EPI_WARPS = 8;
 constexpr int T2_A_TILE = T2_BM * 128;   // bytes of one A tile (hi or lo)
-constexpr int T2_MAX_STAGES = 4;
+constexpr int T2_MAX_STAGES = 6;
 constexpr uint32_t T2_SPIN_LIMIT = 1u << 28;
 constexpr int T2_STG_LD = 36;                        // floats per row of the epilogue staging tile (32 + 4: conflict-free)
 constexpr int T2_STG_BYTES = T2_EPI_WARPS * 32 * T2_STG_LD * 4;
@@ -52,6 +52,10 @@ struct Tc2Cfg {
   int split_b;           // B arrives raw and is split in the kernel (otherwise B_hi / B_lo are loaded pre-split)
   int ntm, ntn, splits, kb_per_split, items;
   uint32_t b_tile, stage_bytes;
+  int a_tmem;            // A hi/lo tiles live in TMEM (tcgen05.st by the splitter, TS-mode MMAs): K-major A only
+  int tstages;           // depth of the TMEM ring of A tiles (64 columns each)
+  int a_tmem_col;        // first TMEM column of that ring
+  uint32_t a_stage;      // bytes of the A part of one shared-memory stage (raw tile, plus the lo tile in SS mode)
   int debug;             // perf experiments only (GET_B200_T2_DEBUG): 1 = main MMA only, 2 = splitter skips its work
 };
 
@@ -99,6 +103,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -162,6 +182,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
   __shared__ __align__(8) uint64_t bar_raw[T2_MAX_STAGES];     // TMA landed (tx bytes)
   __shared__ __align__(8) uint64_t bar_ready[T2_MAX_STAGES];   // hi/lo tiles complete (128 splitter arrivals)
   __shared__ __align__(8) uint64_t bar_empty[T2_MAX_STAGES];   // MMAs that read the stage retired (tcgen05.commit)
+  __shared__ __align__(8) uint64_t bar_tfree[T2_MAX_STAGES];   // TS mode: MMAs that read a TMEM A stage retired
   __shared__ __align__(8) uint64_t bar_accf[2];                // accumulator set complete (tcgen05.commit)
   __shared__ __align__(8) uint64_t bar_acce[2];                // accumulator set drained (all epilogue threads arrive)
   __shared__ uint32_t tmem_holder;
@@ -175,10 +196,11 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
   const uint32_t smem_base = smem_u32(smem);
 
   if (tid == 0) {
-    for (int s = 0; s < cfg.stages; ++s) {
+    for (int s = 0; s < T2_MAX_STAGES; ++s) {
       mbar_init(&bar_raw[s], 1);
       mbar_init(&bar_ready[s], 128);
       mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_tfree[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_accf[b], 1);
@@ -217,7 +239,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           mbar_wait(&bar_empty[stage], phase ^ 1);
           if (kb == kb0) T2_DBG(0, it * 2); if (kb == kb1 - 1) T2_DBG(0, it * 2 + 1);
           const uint32_t sa = smem_base + (uint32_t)stage * cfg.stage_bytes;
-          const uint32_t sbh = sa + 2u * T2_A_TILE, sbl = sbh + cfg.b_tile;
+          const uint32_t sbh = sa + cfg.a_stage, sbl = sbh + cfg.b_tile;
           mbar_arrive_expect_tx(&bar_raw[stage], tx);
           if (cfg.a_mn) {
 #pragma unroll
@@ -247,7 +269,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
       const uint32_t a_lbo = cfg.a_mn ? 4096u : 16u, b_lbo = cfg.b_mn ? 4096u : 16u;
       const uint32_t a_sbo = cfg.a_mn ? 512u : 1024u, b_sbo = cfg.b_mn ? 512u : 1024u;
       const uint32_t a_lt = cfg.a_mn ? 1u : 2u, b_lt = cfg.b_mn ? 1u : 2u;
-      int stage = 0, acc = 0;
+      int stage = 0, acc = 0, tstage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int it = 0; it < n_my; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
@@ -265,8 +287,22 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           if (kb == kb0) T2_DBG(1, it * 3 + 1);
           const uint32_t a_hi = smem_base + (uint32_t)stage * cfg.stage_bytes;
           const uint32_t a_lo = a_hi + T2_A_TILE;
-          const uint32_t b_hi = a_lo + T2_A_TILE;
+          const uint32_t b_hi = a_hi + cfg.a_stage;
           const uint32_t b_lo = b_hi + cfg.b_tile;
+          if (cfg.a_tmem) {
+            const uint32_t ta_hi = tmem_base + (uint32_t)(cfg.a_tmem_col + tstage * 64);
+            const uint32_t ta_lo = ta_hi + 32u;
+#pragma unroll
+            for (int ks = 0; ks < T2_BK / 8; ++ks) {
+              const uint64_t dbh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt), dbl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+              const uint32_t first = (kb > kb0 || ks > 0) ? 1u : 0u;
+              umma_tf32_ts(d_main, ta_hi + ks * 8u, dbh, idesc, first);
+              umma_tf32_ts(d_small, ta_hi + ks * 8u, dbl, idesc, first);
+              umma_tf32_ts(d_small, ta_lo + ks * 8u, dbh, idesc, 1u);
+            }
+            umma_commit(&bar_tfree[tstage]);
+            if (++tstage == cfg.tstages) tstage = 0;
+          } else {
 #pragma unroll
           for (int ks = 0; ks < T2_BK / 8; ++ks) {
             const uint64_t dah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
@@ -278,6 +314,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
               umma_tf32(d_small, dah, dbl, idesc, first);
               umma_tf32(d_small, dal, dbh, idesc, 1u);
             }
+          }
           }
           umma_commit(&bar_empty[stage]);
           if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
@@ -296,8 +333,8 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
   } else if (warp < 6) {
     // =========================================== splitter ===============================================
     const int t = tid - 64;   // 0..127
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, tstage = 0;
+    uint32_t phase = 0, tphase = 0;
     constexpr int a_chunks = T2_A_TILE / 16 / 128;                   // 16-byte chunks per thread in the A tile
     const int b_chunks = cfg.split_b ? (int)(cfg.b_tile / 16) : 0;   // total chunks of the B tile
     for (int it = 0; it < n_my; ++it) {
@@ -309,7 +346,34 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
         if (t == 0 && kb == kb0) T2_DBG(3, it * 2); if (t == 0 && kb == kb1 - 1) T2_DBG(3, it * 2 + 1);
         const uint32_t a_hi = smem_base + (uint32_t)stage * cfg.stage_bytes;
         const uint32_t a_lo = a_hi + T2_A_TILE;
-        if (cfg.debug != 2 && cfg.debug != 3) {
+        if (cfg.a_tmem) {
+          // this thread owns row `trow` of the tile: 128 bytes of the K-major SW128 tile -> hi / lo -> its TMEM lane
+          const int trow = (warp & 3) * 32 + lane;
+          const uint32_t rbase = a_hi + (uint32_t)trow * 128u;
+          const uint32_t sw = (uint32_t)(trow & 7);
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cfg.a_tmem_col + tstage * 64);
+          mbar_wait(&bar_tfree[tstage], tphase ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = lds128(rbase + (((uint32_t)(h * 4 + c) ^ sw) << 4));
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 h4, l4;
+              split4(v[c], h4, l4);
+              hi[c * 4 + 0] = h4.x; hi[c * 4 + 1] = h4.y; hi[c * 4 + 2] = h4.z; hi[c * 4 + 3] = h4.w;
+              lo[c * 4 + 0] = l4.x; lo[c * 4 + 1] = l4.y; lo[c * 4 + 2] = l4.z; lo[c * 4 + 3] = l4.w;
+            }
+            tmem_st16(ta + (uint32_t)(h * 16), hi);
+            tmem_st16(ta + 32u + (uint32_t)(h * 16), lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          if (++tstage == cfg.tstages) { tstage = 0; tphase ^= 1; }
+        } else if (cfg.debug != 2 && cfg.debug != 3) {
           float4 v[a_chunks];
 #pragma unroll
           for (int i = 0; i < a_chunks; ++i) v[i] = lds128(a_hi + (uint32_t)(t + i * 128) * 16u);
@@ -323,7 +387,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           }
         }
         if (cfg.split_b) {
-          const uint32_t b_hi = a_lo + T2_A_TILE;
+          const uint32_t b_hi = a_hi + cfg.a_stage;
           const uint32_t b_lo = b_hi + cfg.b_tile;
           for (int c = t; c < b_chunks; c += 128) {
             const uint32_t off = (uint32_t)c * 16u;
@@ -569,34 +633,61 @@ static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
   cfg.kb_per_split = (cfg.kblocks_total + splits - 1) / splits;
   cfg.splits = (cfg.kblocks_total + cfg.kb_per_split - 1) / cfg.kb_per_split;
   if (cfg.splits > 1 && !d->workspace) return 1;
-  // n tiling: two accumulator sets (main + small) x two buffers must fit 512 TMEM columns when the CTA handles several items
+  // Optional: A hi/lo tiles in TMEM (TS-mode MMAs), K-major A with pre-split B only.
+  // Measured on B200 (profiles/): a TS-mode tf32 MMA costs ~128 cycles whatever N is, an SS-mode one 128*N/256, so at
+  // the N <= 160 tiles of this model SS mode wins; TS mode stays available for experiments (GET_B200_T2_TS=1).
+  static int want_ts = -1;
+  if (want_ts < 0) {
+    const char* e = getenv("GET_B200_T2_TS");
+    want_ts = e ? atoi(e) : 0;
+  }
+  cfg.a_tmem = (want_ts && !cfg.a_mn && !cfg.split_b) ? 1 : 0;
+  // n tiling. TMEM budget (512 columns): accumulator sets (main + small = 2*BN columns each; two sets when the CTA runs
+  // several items so that the epilogue overlaps the next main loop) + in TS mode >= 2 A stages of 64 columns.
   int best_nt = 0;
   double best_cost = 1e30;
-  for (int nt = 1; nt <= 8; ++nt) {
-    const int bn = t2_pad((p.N + nt - 1) / nt, q);
-    if (bn > 256 || bn < 16) continue;
-    if ((nt - 1) * bn >= p.N) continue;
-    const int64_t items = (int64_t)cfg.ntm * nt * cfg.splits;
-    const int64_t rounds = (items + 147) / 148;
-    if (rounds > 1 && bn > 128) continue;                     // double-buffered accumulators need 4*bn <= 512
-    const double cost = (double)rounds * (bn + 48.0);
-    if (cost < best_cost) { best_cost = cost; best_nt = nt; }
+  for (int pass = 0; pass < 2 && best_nt == 0; ++pass) {
+    if (pass == 1) cfg.a_tmem = 0;                          // no TS tiling fits: fall back to SS mode
+    for (int nt = 1; nt <= 8; ++nt) {
+      const int bn = t2_pad((p.N + nt - 1) / nt, q);
+      if (bn > 256 || bn < 16) continue;
+      if ((nt - 1) * bn >= p.N) continue;
+      const int64_t items = (int64_t)cfg.ntm * nt * cfg.splits;
+      const int64_t rounds = (items + 147) / 148;
+      const int bufs = rounds > 1 ? 2 : 1;
+      const int cols = bufs * 2 * bn + (cfg.a_tmem ? 2 * 64 : 0);
+      if (cols > 512) continue;
+      const double cost = (double)rounds * (bn + 48.0);
+      if (cost < best_cost) { best_cost = cost; best_nt = nt; }
+    }
   }
   if (best_nt == 0) return 1;
   if (d->tc_n_tiles > 0) {
     const int bn = t2_pad((p.N + d->tc_n_tiles - 1) / d->tc_n_tiles, q);
-    if (bn <= 256 && bn >= 16 && (d->tc_n_tiles - 1) * bn < p.N) best_nt = d->tc_n_tiles;
+    const int64_t rounds = ((int64_t)cfg.ntm * d->tc_n_tiles * cfg.splits + 147) / 148;
+    const int cols = (rounds > 1 ? 2 : 1) * 2 * bn + (cfg.a_tmem ? 2 * 64 : 0);
+    if (bn <= 256 && bn >= 16 && (d->tc_n_tiles - 1) * bn < p.N && cols <= 512) best_nt = d->tc_n_tiles;
   }
   cfg.ntn = best_nt;
   cfg.BN = t2_pad((p.N + best_nt - 1) / best_nt, q);
   cfg.items = cfg.ntm * cfg.ntn * cfg.splits;
-  cfg.acc_bufs = (4 * cfg.BN <= 512) ? 2 : 1;
-  int tc = 32;
-  while (tc < cfg.acc_bufs * 2 * cfg.BN) tc <<= 1;
-  if (tc > 512) return 1;
-  cfg.tmem_cols = tc;
+  cfg.acc_bufs = (cfg.items > 148) ? 2 : 1;
+  const int acc_cols = cfg.acc_bufs * 2 * cfg.BN;
+  if (cfg.a_tmem) {
+    cfg.tstages = (512 - acc_cols) / 64;
+    if (cfg.tstages > T2_MAX_STAGES) cfg.tstages = T2_MAX_STAGES;
+    if (cfg.tstages < 2) return 1;
+    cfg.a_tmem_col = acc_cols;
+    cfg.tmem_cols = 512;
+  } else {
+    int tc = 32;
+    while (tc < acc_cols) tc <<= 1;
+    if (tc > 512) return 1;
+    cfg.tmem_cols = tc;
+  }
   cfg.b_tile = (uint32_t)cfg.BN * 128u;
-  cfg.stage_bytes = 2u * T2_A_TILE + 2u * cfg.b_tile;
+  cfg.a_stage = cfg.a_tmem ? (uint32_t)T2_A_TILE : 2u * T2_A_TILE;
+  cfg.stage_bytes = cfg.a_stage + 2u * cfg.b_tile;
   int stages = (224 * 1024 - 2048 - T2_STG_BYTES) / (int)cfg.stage_bytes;
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
   if (stages < 2) return 1;

@@ -38,6 +38,7 @@ struct GraphParams {
   uint32_t thr;        // dropout threshold (0 = eval)
   float scale;
   uint32_t seed_s, seed_2;
+  const uint32_t* salt; // device word added to both seeds inside the kernels
   float* score;        // (G,N) or null
   uint8_t* keep_out;   // (G,N)
 };
@@ -49,6 +50,8 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
   const int g = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, H = p.H, NP = p.NP;
+  const uint32_t salt = (FUSED && p.thr) ? __ldg(p.salt) : 0u;
+  const uint32_t seed_s = p.seed_s + salt, seed_2 = p.seed_2 + salt;
   const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
   const float* __restrict__ gx = p.x + (int64_t)g * N * H;
   float* __restrict__ gout = p.out + (int64_t)g * N * H;
@@ -89,10 +92,10 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
           const float4 w = __ldg(reinterpret_cast<const float4*>(p.wp) + q);
           if (p.thr) {
             const uint64_t base = ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)q * 4;
-            f.x = drop_keep(p.seed_s, base + 0, p.thr) ? f.x * p.scale : 0.f;
-            f.y = drop_keep(p.seed_s, base + 1, p.thr) ? f.y * p.scale : 0.f;
-            f.z = drop_keep(p.seed_s, base + 2, p.thr) ? f.z * p.scale : 0.f;
-            f.w = drop_keep(p.seed_s, base + 3, p.thr) ? f.w * p.scale : 0.f;
+            f.x = drop_keep(seed_s, base + 0, p.thr) ? f.x * p.scale : 0.f;
+            f.y = drop_keep(seed_s, base + 1, p.thr) ? f.y * p.scale : 0.f;
+            f.z = drop_keep(seed_s, base + 2, p.thr) ? f.z * p.scale : 0.f;
+            f.w = drop_keep(seed_s, base + 3, p.thr) ? f.w * p.scale : 0.f;
           }
           acc = fmaf(f.x, w.x, acc); acc = fmaf(f.y, w.y, acc);
           acc = fmaf(f.z, w.z, acc); acc = fmaf(f.w, w.w, acc);
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
       } else {
         for (int c = lane; c < H; c += 32) {
           float f = __ldg(row + c);
-          if (p.thr) f = drop_keep(p.seed_s, ((uint64_t)g * N + i) * (uint64_t)H + c, p.thr) ? f * p.scale : 0.f;
+          if (p.thr) f = drop_keep(seed_s, ((uint64_t)g * N + i) * (uint64_t)H + c, p.thr) ? f * p.scale : 0.f;
           acc = fmaf(f, __ldg(p.wp + c), acc);
         }
       }
@@ -174,10 +177,10 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
               float4 f = __ldg(reinterpret_cast<const float4*>(row) + q);
               if (drop2) {
                 const uint64_t base = ((uint64_t)g * N + jj) * (uint64_t)H + (uint64_t)q * 4;
-                f.x = drop_keep(p.seed_2, base + 0, p.thr) ? f.x * p.scale : 0.f;
-                f.y = drop_keep(p.seed_2, base + 1, p.thr) ? f.y * p.scale : 0.f;
-                f.z = drop_keep(p.seed_2, base + 2, p.thr) ? f.z * p.scale : 0.f;
-                f.w = drop_keep(p.seed_2, base + 3, p.thr) ? f.w * p.scale : 0.f;
+                f.x = drop_keep(seed_2, base + 0, p.thr) ? f.x * p.scale : 0.f;
+                f.y = drop_keep(seed_2, base + 1, p.thr) ? f.y * p.scale : 0.f;
+                f.z = drop_keep(seed_2, base + 2, p.thr) ? f.z * p.scale : 0.f;
+                f.w = drop_keep(seed_2, base + 3, p.thr) ? f.w * p.scale : 0.f;
               }
               acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
               acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
               const int c = lane + (u * 4 + e) * 32;
               if (c < H) {
                 float f = __ldg(row + c);
-                if (drop2) f = drop_keep(p.seed_2, ((uint64_t)g * N + jj) * (uint64_t)H + c, p.thr) ? f * p.scale : 0.f;
+                if (drop2) f = drop_keep(seed_2, ((uint64_t)g * N + jj) * (uint64_t)H + c, p.thr) ? f * p.scale : 0.f;
                 a4[e] = fmaf(wj, f, a4[e]);
               }
             }
@@ -277,6 +280,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
   const int g = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, H = p.H, HQ = H >> 2;
+  const uint32_t salt = (FUSED && p.thr) ? __ldg(p.salt) : 0u;
+  const uint32_t seed_s = p.seed_s + salt, seed_2 = p.seed_2 + salt;
   float* sF = smem;
   float2* sL = reinterpret_cast<float2*>(sF + (size_t)N * H);      // N*N entries {offset bits, weight}
   float* sA = reinterpret_cast<float*>(sL);                        // dense adjacency (first half of the list region)
@@ -368,9 +373,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
             if (p.thr) {
               const uint64_t base = ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)(lane + u * 32) * 4;
               float4 f2 = f;
-              drop_apply4(p.seed_2, base, p.thr, p.scale, f2);
+              drop_apply4(seed_2, base, p.thr, p.scale, f2);
               row[u * 32] = f2;
-              drop_apply4(p.seed_s, base, p.thr, p.scale, f);
+              drop_apply4(seed_s, base, p.thr, p.scale, f);
             }
             acc = fmaf(f.x, wq[u].x, acc); acc = fmaf(f.y, wq[u].y, acc);
             acc = fmaf(f.z, wq[u].z, acc); acc = fmaf(f.w, wq[u].w, acc);
@@ -595,7 +600,7 @@ extern "C" int get_gsl_fused_f32(const float* adj, const float* F, const float* 
   p.wp = wp; p.gate = gate; p.k = k;
   p.thr = drop_p > 0.f ? drop_threshold(drop_p) : 0;
   p.scale = 1.0f / (1.0f - drop_p);
-  p.seed_s = seed_scorer; p.seed_2 = seed_layer2;
+  p.seed_s = seed_scorer; p.seed_2 = seed_layer2; p.salt = dropout_salt_ptr();
   p.score = score; p.keep_out = keep;
   return launch_graph(p, true, (cudaStream_t)stream, "get_gsl_fused_f32");
 }

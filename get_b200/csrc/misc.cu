@@ -1,6 +1,7 @@
 // Element-wise / segment kernels of the GET hot path and the library bookkeeping.
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -17,15 +18,30 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+const uint32_t* dropout_salt_ptr() {
+  static uint32_t* salt = nullptr;   // one word per process (one process per GPU); allocated on first use, never freed
+  static std::once_flag once;
+  std::call_once(once, [] {
+    uint32_t* ptr = nullptr;
+    if (cudaMalloc(&ptr, 256) == cudaSuccess && cudaMemset(ptr, 0, 256) == cudaSuccess) salt = ptr;
+    else (void)cudaGetLastError();
+  });
+  return salt;
+}
+
 // ---- GGNN backward, element-wise stage (reference forward Models/BiDAF/wrapper.py:194-206)
 __global__ void __launch_bounds__(256) ggnn_gate_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z,
                                                             const float* __restrict__ h, const float* __restrict__ x,
-                                                            int64_t numel, float* __restrict__ dhp,
+                                                            int M, int H, int64_t ld_g, float* __restrict__ dhp,
                                                             float* __restrict__ dzp, float* __restrict__ dx, int vec) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= numel) return;
+  // inputs and dx are (M, H) contiguous; dhp / dzp are (M, H) views with row stride ld_g (columns of the [dz'|dr'|dh'] buffer)
+  const int hq = (H + 3) >> 2;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (int64_t)M * hq) return;
+  const int m = (int)(q / hq), c = (int)(q % hq) * 4;
+  const int64_t i = (int64_t)m * H + c, o = (int64_t)m * ld_g + c;
   float d[4], zz[4], hh[4], xx[4], o0[4], o1[4], o2[4];
-  const int nvalid = (int)min((int64_t)4, numel - i);
+  const int nvalid = min(4, H - c);
   if (vec) {
     float4 a = *reinterpret_cast<const float4*>(dout + i); d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
     a = *reinterpret_cast<const float4*>(z + i); zz[0] = a.x; zz[1] = a.y; zz[2] = a.z; zz[3] = a.w;
@@ -44,11 +60,11 @@ __global__ void __launch_bounds__(256) ggnn_gate_bwd_kernel(const float* __restr
     o2[e] = d[e] * (1.0f - zz[e]);
   }
   if (vec) {
-    *reinterpret_cast<float4*>(dhp + i) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-    *reinterpret_cast<float4*>(dzp + i) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<float4*>(dhp + o) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+    *reinterpret_cast<float4*>(dzp + o) = make_float4(o1[0], o1[1], o1[2], o1[3]);
     *reinterpret_cast<float4*>(dx + i) = make_float4(o2[0], o2[1], o2[2], o2[3]);
   } else {
-    for (int e = 0; e < nvalid; ++e) { dhp[i + e] = o0[e]; dzp[i + e] = o1[e]; dx[i + e] = o2[e]; }
+    for (int e = 0; e < nvalid; ++e) { dhp[o + e] = o0[e]; dzp[o + e] = o1[e]; dx[i + e] = o2[e]; }
   }
 }
 
@@ -131,9 +147,40 @@ __global__ void __launch_bounds__(256) masked_mean_bwd_kernel(const float* __res
 }
 
 __global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, int64_t numel, uint32_t thr,
-                                                           float scale, uint32_t seed) {
+                                                           float scale, uint32_t seed, const uint32_t* __restrict__ salt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < numel) out[i] = drop_keep(seed, (uint64_t)i, thr) ? scale : 0.f;
+  if (i < numel) out[i] = drop_keep(seed + __ldg(salt), (uint64_t)i, thr) ? scale : 0.f;
+}
+
+__global__ void salt_kernel(uint32_t* salt, uint32_t value, int advance) {
+  *salt = advance ? (*salt) * 1664525u + 1013904223u : value;
+}
+
+// out[r, :] = dropout(src[idx ? idx[r] : r, :]), mask index r*W + c (the A operand of the input projection of a GGNN:
+// embedding gather gbss.py:100,150 + nn.Dropout wrapper.py:189-190, materialised once for forward AND weight gradient)
+__global__ void __launch_bounds__(256) rows_gather_dropout_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                                  const int64_t* __restrict__ idx, int R, int W,
+                                                                  uint32_t thr, float scale, uint32_t seed,
+                                                                  const uint32_t* __restrict__ salt,
+                                                                  float* __restrict__ out, int64_t ld_out, int vec) {
+  const uint32_t sd = seed + (thr ? __ldg(salt) : 0u);
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const float* s = src + (idx ? idx[r] : (int64_t)r) * ld_src;
+    float* d = out + (int64_t)r * ld_out;
+    if (vec) {
+      for (int q = threadIdx.x; q < (W >> 2); q += blockDim.x) {
+        float4 f = __ldg(reinterpret_cast<const float4*>(s) + q);
+        if (thr) drop_apply4(sd, (uint64_t)r * (uint64_t)W + (uint64_t)q * 4, thr, scale, f);
+        reinterpret_cast<float4*>(d)[q] = f;
+      }
+    } else {
+      for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        float f = __ldg(s + c);
+        if (thr) f = drop_keep(sd, (uint64_t)r * (uint64_t)W + c, thr) ? f * scale : 0.f;
+        d[c] = f;
+      }
+    }
+  }
 }
 
 // ---- mean cross-entropy + dlogits (reference losses.py:29-32); one warp, B is a few hundred at most
@@ -170,14 +217,15 @@ __global__ void __launch_bounds__(32) cross_entropy_kernel(const float* __restri
 
 using namespace getb;
 
-extern "C" int get_ggnn_gate_bwd_f32(const float* dout, const float* z, const float* h, const float* x, int64_t numel,
-                                     float* dhp, float* dzp, float* dx, void* stream) {
+extern "C" int get_ggnn_gate_bwd_f32(const float* dout, const float* z, const float* h, const float* x, int M, int H,
+                                     int64_t ld_g, float* dhp, float* dzp, float* dx, void* stream) {
   GETB_REQUIRE(dout && z && h && x && dhp && dzp && dx, "get_ggnn_gate_bwd_f32: null pointer");
-  if (numel <= 0) return 0;
-  const int vec = (numel % 4 == 0) && aligned16(dout) && aligned16(z) && aligned16(h) && aligned16(x) &&
+  GETB_REQUIRE(ld_g >= H, "get_ggnn_gate_bwd_f32: ld_g must be >= H");
+  if (M <= 0 || H <= 0) return 0;
+  const int vec = (H % 4 == 0) && (ld_g % 4 == 0) && aligned16(dout) && aligned16(z) && aligned16(h) && aligned16(x) &&
                   aligned16(dhp) && aligned16(dzp) && aligned16(dx);
-  ggnn_gate_bwd_kernel<<<ceil_div((numel + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(dout, z, h, x, numel, dhp,
-                                                                                         dzp, dx, vec);
+  const int64_t nq = (int64_t)M * ((H + 3) / 4);
+  ggnn_gate_bwd_kernel<<<ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(dout, z, h, x, M, H, ld_g, dhp, dzp, dx, vec);
   GETB_CHECK_LAUNCH("get_ggnn_gate_bwd_f32");
   return 0;
 }
@@ -247,8 +295,48 @@ extern "C" int get_dropout_mask_f32(float* out, int64_t numel, float p, uint32_t
   GETB_REQUIRE(out && p >= 0.f && p < 1.f, "get_dropout_mask_f32: bad arguments");
   if (numel <= 0) return 0;
   dropout_mask_kernel<<<ceil_div(numel, 256), 256, 0, (cudaStream_t)stream>>>(out, numel, drop_threshold(p),
-                                                                             1.0f / (1.0f - p), seed);
+                                                                             1.0f / (1.0f - p), seed, dropout_salt_ptr());
   GETB_CHECK_LAUNCH("get_dropout_mask_f32");
+  return 0;
+}
+
+extern "C" int get_dropout_salt_set(uint32_t value, void* stream) {
+  uint32_t* s = const_cast<uint32_t*>(dropout_salt_ptr());
+  GETB_REQUIRE(s != nullptr, "get_dropout_salt_set: cannot allocate the salt word");
+  salt_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s, value, 0);
+  GETB_CHECK_LAUNCH("get_dropout_salt_set");
+  return 0;
+}
+
+extern "C" int get_dropout_salt_advance(void* stream) {
+  uint32_t* s = const_cast<uint32_t*>(dropout_salt_ptr());
+  GETB_REQUIRE(s != nullptr, "get_dropout_salt_advance: cannot allocate the salt word");
+  salt_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s, 0u, 1);
+  GETB_CHECK_LAUNCH("get_dropout_salt_advance");
+  return 0;
+}
+
+extern "C" int get_dropout_salt_get(uint32_t* host_value) {
+  GETB_REQUIRE(host_value != nullptr, "get_dropout_salt_get: null pointer");
+  const uint32_t* s = dropout_salt_ptr();
+  GETB_REQUIRE(s != nullptr, "get_dropout_salt_get: cannot allocate the salt word");
+  cudaError_t e = cudaMemcpy(host_value, s, sizeof(uint32_t), cudaMemcpyDeviceToHost);   // synchronises: tests only
+  if (e != cudaSuccess) {
+    getb::set_error("get_dropout_salt_get: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+extern "C" int get_rows_gather_dropout_f32(const float* src, int64_t ld_src, const int64_t* idx, int R, int W, float p,
+                                           uint32_t seed, float* out, int64_t ld_out, void* stream) {
+  GETB_REQUIRE(src && out && p >= 0.f && p < 1.f, "get_rows_gather_dropout_f32: bad arguments");
+  if (R <= 0 || W <= 0) return 0;
+  const int vec = (W % 4) == 0 && (ld_src % 4) == 0 && (ld_out % 4) == 0 && aligned16(src) && aligned16(out);
+  const int grid = R < 148 * 16 ? R : 148 * 16;
+  rows_gather_dropout_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, ld_src, idx, R, W, p > 0.f ? drop_threshold(p) : 0u,
+                                                                    1.0f / (1.0f - p), seed, dropout_salt_ptr(), out, ld_out, vec);
+  GETB_CHECK_LAUNCH("get_rows_gather_dropout_f32");
   return 0;
 }
 

@@ -28,8 +28,10 @@ def drop_threshold(p: float) -> int:
     return int(np.float32(p) * np.float32(65536.0))
 
 
-def keep_mask(numel: int, p: float, seed: int, device="cpu") -> torch.Tensor:
-    """float32 (numel,) tensor: 1/(1-p) where element i is kept, 0 where it is dropped."""
+def keep_mask(numel: int, p: float, seed: int, device="cpu", salt: int = 0) -> torch.Tensor:
+    """float32 (numel,) tensor: 1/(1-p) where element i is kept, 0 where it is dropped. `salt` = the device salt word
+    (get_dropout_salt_*), 0 unless a captured training step advanced it."""
+    seed = (seed + salt) & 0xFFFFFFFF
     if p <= 0:
         return torch.ones(numel, dtype=torch.float32, device=device)
     idx = np.arange(numel, dtype=np.uint64)

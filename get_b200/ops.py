@@ -75,12 +75,23 @@ _split_cache = {}
 _SPLIT_CACHE_MAX = 512
 
 
+_split_epoch = 0
+
+
+def begin_step_capture():
+    """Call at the head of a training step that is being captured into a CUDA graph: the weights differ at every
+    replay, so every weight must be re-split INSIDE the captured step (first use), whatever its version counter says."""
+    global _split_epoch
+    _split_epoch += 1
+
+
 def split_weight(b: torch.Tensor):
     """(hi, lo) k-contiguous TF32 split of a weight view b (logical (N, K), any strides), cached per
-    (storage address, shape, strides) and refreshed when the parameter's version counter moves (optimizer step)."""
+    (storage address, shape, strides) and refreshed when the parameter's version counter moves (optimizer step) or a
+    captured step begins (begin_step_capture)."""
     key = (b.data_ptr(), tuple(b.shape), tuple(b.stride()))
     ent = _split_cache.get(key)
-    ver = b._version
+    ver = (b._version, _split_epoch)
     if ent is not None and ent[0] == ver:
         return ent[1], ent[2]
     lib = _lib.load()
@@ -100,6 +111,34 @@ def split_weight(b: torch.Tensor):
     if len(_split_cache) > _SPLIT_CACHE_MAX:
         _split_cache.pop(next(iter(_split_cache)))
     return hi, lo
+
+
+def dropout_salt_set(value: int):
+    _lib.check(_lib.load().get_dropout_salt_set(int(value) & 0xFFFFFFFF, _stream()), "get_dropout_salt_set")
+
+
+def dropout_salt_advance():
+    _lib.check(_lib.load().get_dropout_salt_advance(_stream()), "get_dropout_salt_advance")
+
+
+def dropout_salt_get() -> int:
+    v = C.c_uint32(0)
+    _lib.check(_lib.load().get_dropout_salt_get(C.byref(v)), "get_dropout_salt_get")
+    return int(v.value)
+
+
+def rows_gather_dropout(src: torch.Tensor, idx: Optional[torch.Tensor], rows: int, p: float, seed: int) -> torch.Tensor:
+    """out (rows, W) = dropout(src[idx]) (idx int64 or None = identity); see get_rows_gather_dropout_f32."""
+    lib = _lib.load()
+    _chk_f32(src, "src")
+    assert src.dim() == 2 and src.stride(1) == 1
+    W = src.shape[1]
+    out = torch.empty((rows, W), dtype=torch.float32, device=src.device)
+    if idx is not None:
+        assert idx.dtype == torch.int64 and idx.is_cuda and idx.is_contiguous() and idx.numel() == rows
+    _lib.check(lib.get_rows_gather_dropout_f32(src.data_ptr(), src.stride(0), _ptr(idx), rows, W, float(p), seed & 0xFFFFFFFF,
+                                               out.data_ptr(), W, _stream()), "get_rows_gather_dropout_f32")
+    return out
 
 
 def new_seed() -> int:
@@ -273,17 +312,16 @@ class GGNNLayerFn(torch.autograd.Function):
         adj = adj.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         x = torch.empty((M, H), **f32)
-        drop = dict(drop_p=p_drop, drop_seed=seed, drop_cols=Din) if p_drop > 0 else {}
+        # the projection input (embedding gather and / or dropout) is materialised once: the forward projection and the
+        # weight gradient dWp then both read plain (M, Din) tiles through TMA
         if feat is not None:
             feat2d = _rows2d(feat)
-            gemm([(feat2d, Wp)], x, tc=True, **drop)
-            rowidx = None
+            xd = rows_gather_dropout(feat2d, None, M, p_drop, seed) if p_drop > 0 else feat2d
         else:
-            rowidx = ids.reshape(-1).to(torch.int64).contiguous()
-            # logical A = table rows gathered by rowidx; shape bookkeeping through an expanded view
             _chk_f32(table, "table")
-            a_view = Raw(table.data_ptr(), table.stride(0), 0, (M, Din))
-            gemm([(a_view, Wp)], x, rowidx=rowidx, tc=True, **drop)
+            rowidx = ids.reshape(-1).to(torch.int64).contiguous()
+            xd = rows_gather_dropout(table, rowidx, M, p_drop, seed)
+        gemm([(xd, Wp)], x, tc=True)
         a = torch.empty((M, H), **f32)
         if pre_agg is not None:
             gemm([(_rows2d(pre_agg), Wp)], a, tc=True)
@@ -298,25 +336,26 @@ class GGNNLayerFn(torch.autograd.Function):
         gemm([(a, Wr0), (x, Wr1)], r, epilogue=EPI_SIGMOID, bias0=br0, bias1=br1, aux0=x, out1=rx, tc=True)
         gemm([(a, Wh0), (rx, Wh1)], out, epilogue=EPI_TANH_BLEND, bias0=bh0, bias1=bh1, aux0=z, aux1=x, out1=h,
              tc=True)
-        ctx.save_for_backward(adj, feat, table, rowidx, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1)
-        ctx.p_drop, ctx.seed, ctx.dims = p_drop, seed, (G, N, H, Din)
+        ctx.save_for_backward(adj, xd, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1)
+        ctx.p_drop, ctx.seed, ctx.dims, ctx.has_feat = p_drop, seed, (G, N, H, Din), feat is not None
         return out.view(G, N, H)
 
     @staticmethod
     def backward(ctx, dout):
-        adj, feat, table, rowidx, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1 = ctx.saved_tensors
+        adj, xd, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1 = ctx.saved_tensors
         G, N, H, Din = ctx.dims
         M = G * N
         dev = dout.device
         f32 = dict(dtype=torch.float32, device=dev)
         lib = _lib.load()
         dout = dout.contiguous().view(M, H)
-        dhp = torch.empty((M, H), **f32)
-        dzp = torch.empty((M, H), **f32)
-        drp = torch.empty((M, H), **f32)
+        # gate gradients live side by side in one (M, 3H) buffer [dz' | dr' | dh'] so that the weight gradients that
+        # share an activation operand are ONE contraction each: [dz'|dr'|dh']^T a and [dz'|dr']^T x
+        dg = torch.empty((M, 3 * H), **f32)
+        dzp, drp, dhp = dg[:, :H], dg[:, H:2 * H], dg[:, 2 * H:]
         dx = torch.empty((M, H), **f32)
         da = torch.empty((M, H), **f32)
-        _lib.check(lib.get_ggnn_gate_bwd_f32(dout.data_ptr(), z.data_ptr(), h.data_ptr(), x.data_ptr(), M * H,
+        _lib.check(lib.get_ggnn_gate_bwd_f32(dout.data_ptr(), z.data_ptr(), h.data_ptr(), x.data_ptr(), M, H, 3 * H,
                                              dhp.data_ptr(), dzp.data_ptr(), dx.data_ptr(), _stream()),
                    "get_ggnn_gate_bwd_f32")
         # d(rx) = dhp @ Wh1 ; drp = d(rx)*x*r*(1-r) ; dx += d(rx)*r
@@ -328,42 +367,30 @@ class GGNNLayerFn(torch.autograd.Function):
         graph_aggregate(adj, da.view(G, N, H), keep, out=dx.view(G, N, H), transpose=True, accumulate=True)
         need = ctx.needs_input_grad
         grads = [None] * 21
-
-        def wgrad(dg, act):
-            w = torch.empty((H, H), **f32)
-            gemm([(dg.t(), act.t())], w, tc=True, presplit=False)
-            return w
-
         # order of inputs: ... 8:Wp 9:Wz0 10:bz0 11:Wz1 12:bz1 13:Wr0 14:br0 15:Wr1 16:br1 17:Wh0 18:bh0 19:Wh1 20:bh1
-        if need[9]: grads[9] = wgrad(dzp, a)
-        if need[11]: grads[11] = wgrad(dzp, x)
-        if need[13]: grads[13] = wgrad(drp, a)
-        if need[15]: grads[15] = wgrad(drp, x)
-        if need[17]: grads[17] = wgrad(dhp, a)
-        if need[19]: grads[19] = wgrad(dhp, rx)
-        if need[10] or need[12]:
-            g = colsum(dzp)
-            grads[10] = g if need[10] else None
-            grads[12] = g if need[12] else None
-        if need[14] or need[16]:
-            g = colsum(drp)
-            grads[14] = g if need[14] else None
-            grads[16] = g if need[16] else None
-        if need[18] or need[20]:
-            g = colsum(dhp)
-            grads[18] = g if need[18] else None
-            grads[20] = g if need[20] else None
-        drop = dict(drop_p=ctx.p_drop, drop_seed=ctx.seed, drop_cols=Din) if ctx.p_drop > 0 else {}
+        if need[9] or need[13] or need[17]:
+            wa = torch.empty((3 * H, H), **f32)                      # [dWz0; dWr0; dWh0]
+            gemm([(dg.t(), a.t())], wa, tc=True, presplit=False)
+            grads[9], grads[13], grads[17] = wa[:H], wa[H:2 * H], wa[2 * H:]
+        if need[11] or need[15]:
+            wx = torch.empty((2 * H, H), **f32)                      # [dWz1; dWr1]
+            gemm([(dg[:, :2 * H].t(), x.t())], wx, tc=True, presplit=False)
+            grads[11], grads[15] = wx[:H], wx[H:]
+        if need[19]:
+            w = torch.empty((H, H), **f32)
+            gemm([(dhp.t(), rx.t())], w, tc=True, presplit=False)
+            grads[19] = w
+        if any(need[i] for i in (10, 12, 14, 16, 18, 20)):
+            gb = colsum(dg)                                          # [dbz | dbr | dbh]
+            grads[10] = grads[12] = gb[:H]
+            grads[14] = grads[16] = gb[H:2 * H]
+            grads[18] = grads[20] = gb[2 * H:]
         if need[8]:
-            # dWp^T (Din,H) = Xd^T @ dx  (gather + dropout are applied on the A operand)
+            # dWp^T (Din,H) = Xd^T @ dx on the materialised projection input
             wT = torch.empty((Din, H), **f32)
-            if feat is not None:
-                gemm([(_rows2d(feat).t(), dx.t())], wT, tc=True, presplit=False, **drop)
-            else:
-                a_view = Raw(table.data_ptr(), table.stride(0), 0, (M, Din))
-                gemm([(a_view.t(), dx.t())], wT, rowidx=rowidx, **drop)
+            gemm([(xd.t(), dx.t())], wT, tc=True, presplit=False)
             grads[8] = wT.t()
-        if feat is not None and need[1]:
+        if ctx.has_feat and need[1]:
             dfeat = torch.empty((M, Din), **f32)
             if ctx.p_drop > 0:
                 gemm([(dx, Wp.t())], dfeat, epilogue=EPI_DROPOUT_OUT, drop_out_p=ctx.p_drop, drop_out_seed=ctx.seed,

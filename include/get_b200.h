@@ -172,11 +172,13 @@ int get_att_pool_bwd_f32(const float* t, const float* right, int64_t ld_right, c
                          int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * GGNN backward, element-wise stage: from dout, z, h, x
- *   dhp = dout*z*(1-h^2) ; dzp = dout*(h-x)*z*(1-z) ; dx = dout*(1-z).       All (M,H) contiguous.
+ * GGNN backward, element-wise stage: from dout, z, h, x  (all (M,H) contiguous)
+ *   dhp = dout*z*(1-h^2) ; dzp = dout*(h-x)*z*(1-z) ; dx = dout*(1-z).
+ * dhp / dzp are (M,H) views with row stride ld_g: columns of the (M,3H) gate-gradient buffer [dz'|dr'|dh'] whose
+ * weight gradients are then single contractions; dx is (M,H) contiguous.
  * ---------------------------------------------------------------------------------------------- */
 int get_ggnn_gate_bwd_f32(const float* dout, const float* z, const float* h, const float* x,
-                          int64_t numel, float* dhp, float* dzp, float* dx, void* stream);
+                          int M, int H, int64_t ld_g, float* dhp, float* dzp, float* dx, void* stream);
 
 /* Column sums out[n] = sum_m a[m*ld + n] (bias gradients), deterministic two-stage reduction.
  * workspace: at least get_colsum_workspace_floats(M, N) floats. */
@@ -205,8 +207,24 @@ int get_masked_mean_fwd_f32(const float* h, const int64_t* ids, const int64_t* l
 int get_masked_mean_bwd_f32(const float* dout, const int64_t* ids, const int64_t* lens, int G, int N, int H,
                             float* dh, void* stream);
 
+/* Input of a GGNN projection materialised once: out[r,:] = dropout(src[idx ? idx[r] : r, :]) -- the embedding gather
+ * (gbss.py:100,150) fused with nn.Dropout (wrapper.py:189-190); mask index r*W + c, keep() as below. idx int64 or NULL.
+ * Forward projection and weight gradient then read the same (R, W) matrix through plain TMA tiles. */
+int get_rows_gather_dropout_f32(const float* src, int64_t ld_src, const int64_t* idx, int R, int W, float p,
+                                uint32_t seed, float* out, int64_t ld_out, void* stream);
+
+/* Dropout salt: one device word per process, added to EVERY dropout seed inside the kernels (effective seed =
+ * seed + salt mod 2^32). It is 0 unless set. A captured CUDA graph replays fixed kernel arguments; recording
+ * get_dropout_salt_advance at the head of the graph (salt <- salt*1664525 + 1013904223) gives every replay fresh masks.
+ * get_dropout_salt_get copies the word to the host (synchronises; tests). */
+int get_dropout_salt_set(uint32_t value, void* stream);
+int get_dropout_salt_advance(void* stream);
+int get_dropout_salt_get(uint32_t* host_value);
+
 /* The dropout keep-mask used by every fused dropout site, materialised (tests / externally supplied masks):
- * out[i] = keep(seed, i) ? 1/(1-p) : 0,  keep(seed,i) = (hash32(i ^ seed) >> 8) * 2^-24 >= p. */
+ * out[i] = keep(seed + salt, i) ? 1/(1-p) : 0. One 32-bit hash serves an aligned pair of elements, 16 bits each:
+ * keep(s, i) = ((mix32(lo32(i>>1)*0x9E3779B1 + hi32(i>>1)*0x632BE5AB + s*0x85EBCA6B + 0x6A09E667) >> 16*(i&1)) & 0xFFFF)
+ *              >= floor(p * 65536)   (csrc/common.cuh; host mirror get_b200/dropout.py). */
 int get_dropout_mask_f32(float* out, int64_t numel, float p, uint32_t seed, void* stream);
 
 /* Mean cross-entropy over claims + gradient w.r.t. logits (losses.py:29-32). logits (B,C), labels (B,) int64.
