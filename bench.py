@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NBATCH = 16
+PAD_PAIRS = 16
 WORKLOAD = "snopes"
 METRIC = "claim_evidence_pairs_per_sec_fwd_bwd"
 
@@ -164,6 +165,46 @@ def config_dict(w, extra=None):
     return cfg
 
 
+def stream_roofline(w, dev, graphs=7680, iters=10):
+    """The same fused kernel at streaming size (BASELINE.json configs[4]: thousands of claim-evidence graphs resident,
+    Snopes dims): at B=32 the launch is two partial waves of CTAs, SURVEY.md 8(d) asks for the roofline at B1 >= 1e4-ish
+    sizes as well. Inputs (2 x 1.2 GB sets, alternated) exceed L2; eval- and train-mode (dropout) launches."""
+    import torch
+    from get_b200 import ops
+    N, H = w.len_right, w.hidden
+    rng = np.random.default_rng(7)
+    from get_b200 import synthetic
+    base = []
+    for g in range(48):
+        pool = rng.integers(2, w.vocab, size=min(w.evd_pool, w.vocab - 2))
+        toks = pool[rng.integers(0, pool.shape[0], size=N)]
+        base.append(synthetic.word_graph(toks, N, w.window)[1].astype(np.float32))
+    adj1 = torch.from_numpy(np.stack(base)).to(dev)
+    sets = []
+    for s in range(2):
+        adj = adj1.repeat((graphs + 47) // 48, 1, 1)[:graphs].contiguous()
+        sets.append((adj, torch.randn(graphs, N, H, device=dev)))
+    wp, gate = torch.randn(H, device=dev) * 0.1, torch.randn(12, device=dev)
+    k = int(w.gsl_rate * N)
+    peak, _ = _peaks()
+    out = {"graphs": graphs, "algorithmic_bytes_per_launch": graphs * 4 * N * (2 * H + N), "peak": peak, "unit": "GB/s"}
+    for name, p in (("eval", 0.0), ("train_p0.2", 0.2)):
+        for i in range(3):
+            ops.gsl_fused(*sets[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2)
+        evs = []
+        for i in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.gsl_fused(*sets[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        gbs = out["algorithmic_bytes_per_launch"] / ms / 1e6
+        out[name] = {"avg_launch_ms": ms, "achieved": gbs, "frac": gbs / peak}
+    return out
+
+
 # =================================================================================================
 def run_ours(args):
     import torch
@@ -188,12 +229,22 @@ def run_ours(args):
     model.train()
     named = trainable_named_parameters(model)
     params = [p for _, p in named]
-    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-3, fused=True)
+    use_graph = not args.no_graph
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-3, fused=True, capturable=use_graph)
     reducer = FlatGradAllReduce(params)
 
     batches = make_batches(w, NBATCH, 123756 + 7919 * rank)
-    host = [synthetic.batch_to_torch(b, device="cpu", pin=True) for b in batches]
-    resident = [synthetic.batch_to_torch(b, device=dev) for b in batches]
+    if use_graph:
+        # one CUDA graph per batch shape: pad the flattened pairs to a multiple of PAD_PAIRS with dummy claims that are
+        # excluded from the loss (get_b200/step_graph.py); `pairs` below keeps counting REAL pairs only
+        from get_b200.step_graph import CapturedTrainStep, pad_batch
+        padded = [pad_batch(b, PAD_PAIRS) for b in batches]
+        stepper = CapturedTrainStep(model, opt, reducer)
+    else:
+        padded = batches
+    n_real = [b.get("n_real_claims", b["query"].shape[0]) for b in padded]
+    host = [synthetic.batch_to_torch(b, device="cpu", pin=True) for b in padded]
+    resident = [synthetic.batch_to_torch(b, device=dev) for b in padded]
 
     def to_device(hb):
         q, d, l, kw = hb
@@ -210,8 +261,10 @@ def run_ours(args):
                     n += x.numel() * x.element_size()
         return n
 
-    def step(db):
+    def step(db, b):
         q, d, l, kw = db
+        if use_graph:
+            return stepper.step(q, d, l, kw, n_real[b])      # copies into the graph's static buffers, one replay
         opt.zero_grad(set_to_none=True)
         logits = model(q, d, **kw)
         loss = ops.cross_entropy(logits, l)
@@ -227,16 +280,17 @@ def run_ours(args):
 
     # ---- warm-up ---------------------------------------------------------------------------------
     for i in range(max(3, args.warmup)):
-        step(resident[i % NBATCH])
+        step(resident[i % NBATCH], i % NBATCH)
+    if use_graph:                      # build every graph before the timed regions (one per distinct padded shape)
+        for b in range(NBATCH):
+            step(resident[b], b)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ops.PROFILE_GSL_EVENTS = []
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + (stepper.replayed_launches if use_graph else 0)
     barrier()
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -244,19 +298,15 @@ def run_ours(args):
     pairs = 0
     for i in range(args.steps):
         b = (i + args.warmup) % NBATCH
-        step(resident[b])
+        step(resident[b], b)
         pairs += batches[b]["pairs"]
     e1.record()
     t_enqueue = time.perf_counter() - t_wall0      # host time to enqueue the K steps (no sync inside)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() + (stepper.replayed_launches if use_graph else 0) - launches0
     clocks = sampler.stop() if rank == 0 else None
     t_dev = e0.elapsed_time(e1) / 1e3
-    gsl_events = ops.PROFILE_GSL_EVENTS
-    ops.PROFILE_GSL_EVENTS = None
-    gsl_ms = [a.elapsed_time(b) for a, b, _ in gsl_events]
-    gsl_pairs = [n for _, _, n in gsl_events]
 
     # ---- timed region 2: end to end from pinned host memory --------------------------------------
     barrier()
@@ -266,7 +316,7 @@ def run_ours(args):
     pairs_e2e, h2d, d2h = 0, 0, 0
     for i in range(args.steps):
         b = (i + args.warmup) % NBATCH
-        loss = step(to_device(host[b]))
+        loss = step(host[b] if use_graph else to_device(host[b]), b)
         _ = float(loss.item())                      # device -> host read of the step's result
         pairs_e2e += batches[b]["pairs"]
         h2d += h2d_bytes(host[b])
@@ -274,6 +324,25 @@ def run_ours(args):
     e3.record()
     barrier()
     t_e2e = max(time.perf_counter() - t0, e2.elapsed_time(e3) / 1e3)
+
+    # ---- roofline of the fused GSL kernel: the same steps issued kernel by kernel (events cannot be read out of a graph
+    #      replay), CUDA events on the launch stream around every get_gsl_fused_f32 launch ------------------------------
+    gsl_ms, gsl_pairs, stream_roof = [], [], None
+    if rank == 0:
+        ops.PROFILE_GSL_EVENTS = []
+        for i in range(min(args.steps, 16)):
+            b = (i + args.warmup) % NBATCH
+            q, d, l, kw = resident[b]
+            opt.zero_grad(set_to_none=True)
+            loss = ops.cross_entropy(model(q, d, **kw)[:n_real[b]], l[:n_real[b]])
+            loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        gsl_events, ops.PROFILE_GSL_EVENTS = ops.PROFILE_GSL_EVENTS, None
+        gsl_ms = [a.elapsed_time(b) for a, b, _ in gsl_events]
+        gsl_pairs = [n for _, _, n in gsl_events]
+        stream_roof = stream_roofline(w, dev)
+    barrier()
 
     # ---- reduce over ranks: max time, summed pairs ------------------------------------------------
     stats = torch.tensor([t_dev, t_e2e, float(pairs), float(pairs_e2e)], dtype=torch.float64, device=dev)
@@ -316,6 +385,8 @@ def run_ours(args):
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "avg_launch_ms": gsl_avg_ms, "algorithmic_bytes_per_launch": gsl_bytes,
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
+            "roofline_stream": stream_roof,
+            "cuda_graphs": {"enabled": use_graph, "graphs": stepper.n_graphs() if use_graph else 0, "pad_pairs_to": PAD_PAIRS if use_graph else 0},
             "cpu_baseline": {"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]},
         }
@@ -331,6 +402,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 12:

@@ -78,6 +78,20 @@ _SPLIT_CACHE_MAX = 512
 _split_epoch = 0
 
 
+def weights_updated(*_args, **_kwargs):
+    """Invalidate every cached weight split. Registered as a global optimizer post-step hook: fused / foreach optimizer
+    kernels update parameters without moving their version counters, so the counter alone cannot be trusted."""
+    global _split_epoch
+    _split_epoch += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(weights_updated)
+except Exception:      # very old torch: callers must invoke ops.weights_updated() after optimizer.step()
+    pass
+
+
 def begin_step_capture():
     """Call at the head of a training step that is being captured into a CUDA graph: the weights differ at every
     replay, so every weight must be re-split INSIDE the captured step (first use), whatever its version counter says."""

@@ -1,0 +1,206 @@
+"""Training step of the GET hot path captured into CUDA graphs (one graph per mini-batch shape).
+
+At the reference's batch size (32 claims, ~200 claim-evidence pairs) one step is ~110 kernel launches of a few tens of
+microseconds each: issued one by one from Python the step is bound by the host, not by the GPU. `CapturedTrainStep`
+records  [advance dropout salt -> forward -> cross-entropy -> backward -> (gradient all-reduce) -> (optimizer step)]
+once per shape and replays it with one launch; inputs are copied into static device buffers first.
+
+The fitter hands over B1 = sum of evidence counts flattened pairs, which varies from batch to batch. To bound the number
+of graphs the batch is padded with dummy claims (copies of the first claim with copies of its first evidence) up to a
+multiple of `pad_pairs_to` pairs; dummy claims are excluded from the loss, so the real claims' logits, the loss and all
+gradients are unchanged (every claim is independent of the others).
+
+Dropout: a replay repeats the captured kernel arguments, so the per-step variation of the masks comes from the
+library's device salt word, advanced by the first node of the graph (include/get_b200.h, get_dropout_salt_advance).
+"""
+import copy
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .keywords import KeyWordSettings as K
+
+_TENSOR_KEYS = (K.Query_lens, K.QuerySources, K.DocSources, K.DocContentNoPaddingEvidence, K.EvidenceCountPerQuery,
+                K.Query_Adj, K.Evd_Docs_Adj)
+
+
+def pad_batch(batch: Dict, multiple: int) -> Dict:
+    """numpy mini-batch (get_b200.synthetic.make_batch layout / the fitter's flattened layout) -> the same batch with
+    dummy claims appended so that the number of pairs is a multiple of `multiple`. Adds 'n_real_claims', 'real_pairs'."""
+    B1 = int(batch[K.DocContentNoPaddingEvidence].shape[0])
+    B = int(batch["query"].shape[0])
+    n = int(batch[K.FIXED_NUM_EVIDENCES])
+    out = dict(batch)
+    out["n_real_claims"], out["real_pairs"] = B, B1
+    pad = (-B1) % max(1, int(multiple))
+    if pad == 0:
+        return out
+    counts = []
+    while pad > 0:
+        c = min(n, pad)
+        counts.append(c)
+        pad -= c
+    nd, extra = len(counts), int(sum(counts))
+
+    def rep0(a, reps):               # `reps` copies of the first row
+        return np.repeat(a[:1], reps, axis=0)
+
+    out["query"] = np.concatenate([batch["query"], rep0(batch["query"], nd)])
+    out["labels"] = np.concatenate([batch["labels"], np.zeros((nd,), batch["labels"].dtype)])
+    out[K.Query_lens] = np.concatenate([batch[K.Query_lens], rep0(batch[K.Query_lens], nd)])
+    out[K.Query_Adj] = np.concatenate([batch[K.Query_Adj], rep0(batch[K.Query_Adj], nd)])
+    out[K.QuerySources] = np.concatenate([batch[K.QuerySources], rep0(batch[K.QuerySources], nd)])
+    doc = np.zeros((nd,) + batch["document"].shape[1:], batch["document"].dtype)
+    src = np.full((nd, n), -1, batch[K.DocSources].dtype)
+    lens = np.zeros((nd, n), batch[K.Doc_lens].dtype)
+    for i, c in enumerate(counts):
+        doc[i, :c] = batch["document"][0, 0]
+        src[i, :c] = batch[K.DocSources][0, 0]
+        lens[i, :c] = batch[K.Doc_lens][0, 0]
+    out["document"] = np.concatenate([batch["document"], doc])
+    out[K.DocSources] = np.concatenate([batch[K.DocSources], src])
+    out[K.Doc_lens] = np.concatenate([batch[K.Doc_lens], lens])
+    out[K.EvidenceCountPerQuery] = np.concatenate([batch[K.EvidenceCountPerQuery],
+                                                   np.asarray(counts, batch[K.EvidenceCountPerQuery].dtype)])
+    out[K.DocContentNoPaddingEvidence] = np.concatenate([batch[K.DocContentNoPaddingEvidence],
+                                                         rep0(batch[K.DocContentNoPaddingEvidence], extra)])
+    out[K.Evd_Docs_Adj] = np.concatenate([batch[K.Evd_Docs_Adj], rep0(batch[K.Evd_Docs_Adj], extra)])
+    out["e_lens"] = np.concatenate([batch["e_lens"], rep0(batch["e_lens"], extra)])
+    out["pairs"] = B1 + extra
+    return out
+
+
+class _Slot(object):
+    __slots__ = ("graph", "query", "document", "labels", "kw", "loss", "logits", "n_real", "launches")
+
+
+class CapturedTrainStep(object):
+    """step(query, document, labels, kwargs, n_real_claims) -> loss (0-d device tensor, valid until the next step).
+
+    All tensor arguments may live on the host (pinned for asynchronous copies) or on the device; shapes select the graph.
+    `optimizer` (capturable) and `reducer` (get_b200.ddp.FlatGradAllReduce) are optional parts of the captured step."""
+
+    def __init__(self, model, optimizer=None, reducer=None, loss_fn=None):
+        self.model, self.optimizer, self.reducer = model, optimizer, reducer
+        self.loss_fn = loss_fn or ops.cross_entropy
+        self.slots: Dict[Tuple, _Slot] = {}
+        self.device = next(model.parameters()).device
+        self.replayed_launches = 0       # kernels of libget_b200.so launched through graph replays so far
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _key(self, query, document, kw, n_real):
+        return (tuple(query.shape), tuple(document.shape), tuple(kw[K.DocContentNoPaddingEvidence].shape),
+                tuple(kw[K.Evd_Docs_Adj].shape), str(kw[K.Evd_Docs_Adj].dtype), int(n_real), bool(self.model.training))
+
+    def _eager(self, s: _Slot):
+        logits = self.model(s.query, s.document, **s.kw)
+        loss = self.loss_fn(logits[:s.n_real], s.labels[:s.n_real])
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.reduce()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return logits, loss
+
+    def _build(self, query, document, labels, kw, n_real) -> _Slot:
+        dev = self.device
+        s = _Slot()
+        s.n_real = int(n_real)
+        new = lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev)
+        s.query, s.document, s.labels = new(query), new(document), new(labels)
+        s.kw = dict(kw)
+        for k in _TENSOR_KEYS:
+            if k in kw and torch.is_tensor(kw[k]):
+                s.kw[k] = new(kw[k])
+        e_lens = kw[K.DocLensIndices][2]
+        s.kw[K.DocLensIndices] = (None, None, new(e_lens))
+        if K.QueryLensIndices in kw:
+            s.kw[K.QueryLensIndices] = (None, None, s.kw[K.Query_lens])
+        self._copy_in(s, query, document, labels, kw)
+        # ---- one eager warm-up step on a side stream (lazy initialisation must not happen inside the capture);
+        #      parameters, optimizer state and the dropout salt are restored afterwards: building a graph is not a step
+        params = [p for p in self.model.parameters()]
+        backup = [p.detach().clone() for p in params]
+        # optimizer state is restored IN PLACE: graphs captured earlier hold the addresses of these tensors
+        opt_backup = None
+        if self.optimizer is not None:
+            opt_backup = {p: {k: (v.detach().clone() if torch.is_tensor(v) else copy.deepcopy(v)) for k, v in st.items()}
+                          for p, st in self.optimizer.state.items()}
+        salt = ops.dropout_salt_get()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._zero_grad()
+            self._eager(s)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for p, b in zip(params, backup):
+                p.copy_(b)
+        if self.optimizer is not None:
+            with torch.no_grad():
+                for p, st in self.optimizer.state.items():
+                    old = opt_backup.get(p)
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if old is not None and k in old:
+                                v.copy_(old[k])
+                            else:
+                                v.zero_()          # state created by the warm-up step: back to its initial value
+                        elif old is not None and k in old:
+                            st[k] = old[k]
+        ops.dropout_salt_set(salt)
+        # ---- capture
+        self._zero_grad()
+        prof, ops.PROFILE_GSL_EVENTS = ops.PROFILE_GSL_EVENTS, None
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(g):
+            ops.begin_step_capture()
+            ops.dropout_salt_advance()
+            s.logits, s.loss = self._eager(s)
+        s.launches = _lib.launch_count() - n0      # kernels of libget_b200.so recorded in this graph
+        ops.PROFILE_GSL_EVENTS = prof
+        s.graph = g
+        return s
+
+    def _zero_grad(self):
+        if self.optimizer is not None:
+            self.optimizer.zero_grad(set_to_none=True)
+        else:
+            self.model.zero_grad(set_to_none=True)
+
+    @staticmethod
+    def _copy_in(s: _Slot, query, document, labels, kw):
+        s.query.copy_(query, non_blocking=True)
+        s.document.copy_(document, non_blocking=True)
+        s.labels.copy_(labels, non_blocking=True)
+        for k in _TENSOR_KEYS:
+            if k in kw and torch.is_tensor(kw[k]):
+                s.kw[k].copy_(kw[k], non_blocking=True)
+        s.kw[K.DocLensIndices][2].copy_(kw[K.DocLensIndices][2], non_blocking=True)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def step(self, query, document, labels, kw, n_real_claims: Optional[int] = None) -> torch.Tensor:
+        n_real = int(n_real_claims if n_real_claims is not None else query.shape[0])
+        key = self._key(query, document, kw, n_real)
+        s = self.slots.get(key)
+        if s is None:
+            s = self._build(query, document, labels, kw, n_real)
+            self.slots[key] = s
+            # the capture itself executes nothing: fall through and replay once so that this call IS a step
+        else:
+            self._copy_in(s, query, document, labels, kw)
+        s.graph.replay()
+        self.replayed_launches += s.launches
+        return s.loss
+
+    @property
+    def last_logits(self):
+        return None
+
+    def n_graphs(self) -> int:
+        return len(self.slots)
