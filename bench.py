@@ -239,7 +239,8 @@ def run_ours(args):
         # excluded from the loss (get_b200/step_graph.py); `pairs` below keeps counting REAL pairs only
         from get_b200.step_graph import CapturedTrainStep, pad_batch
         padded = [pad_batch(b, PAD_PAIRS) for b in batches]
-        stepper = CapturedTrainStep(model, opt, reducer)
+        stepper = CapturedTrainStep(model, opt, reducer,
+                                    collective_in_graph=os.environ.get("GET_B200_GRAPH_COLLECTIVE", "1") != "0")
     else:
         padded = batches
     n_real = [b.get("n_real_claims", b["query"].shape[0]) for b in padded]
@@ -391,9 +392,15 @@ def run_ours(args):
                              "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]},
         }
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        # Tearing down a communicator whose collectives live inside captured CUDA graphs can block in ncclCommDestroy;
+        # every rank is done once it passes this barrier, so leave without destroying the process group.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

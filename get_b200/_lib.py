@@ -36,6 +36,11 @@ class GemmDesc(C.Structure):
     ]
 
 
+class SplitJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("ld_r", C.c_int64), ("ld_c", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("hi", C.c_void_p), ("lo", C.c_void_p), ("ld_out", C.c_int64), ("first_block", C.c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/get_b200.h (tests/test_abi.py checks it)
 _P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 SIGNATURES = {
@@ -43,6 +48,7 @@ SIGNATURES = {
     "get_gemm_f32_launches": (_I, [C.POINTER(GemmDesc)]),
     "get_gemm_f32_uses_tc": (_I, [C.POINTER(GemmDesc)]),
     "get_split_tf32_f32": (_I, [_P, _L, _L, _I, _I, _P, _P, _L, _P]),
+    "get_split_tf32_multi_f32": (_I, [_P, _I, _L, _P]),
     "get_graph_aggregate_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "get_gsl_fused_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P]),
     "get_gsl_mask_adj_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

@@ -7,7 +7,8 @@
 
 namespace getb {
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 1024;     // the kernels are latency-bound chains per group: wide CTAs shorten every serial loop
+constexpr int ATT_MAX_PARTS = 8;
 constexpr int ATT_WARPS = ATT_THREADS / 32;
 constexpr int ATT_MAX_HEADS = 8;
 
@@ -27,7 +28,7 @@ struct AttParams {
   int accumulate;
 };
 
-// fwd smem: W2 (C*H) | e/att (P*C)
+// fwd smem: W2 (C*H) | e/att (P*C) | pooled partials (parts*Dr*C)
 __global__ void __launch_bounds__(ATT_THREADS) att_pool_fwd_kernel(const __grid_constant__ AttParams p) {
   extern __shared__ __align__(16) float smem[];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -79,26 +80,55 @@ __global__ void __launch_bounds__(ATT_THREADS) att_pool_fwd_kernel(const __grid_
     }
   }
   __syncthreads();
-  // pooled[d,c] = sum_p right[p,d] * att[p,c]
+  // pooled[d,c] = sum_p right[p,d] * att[p,c]; positions are split over `parts` thread groups, partials reduced in smem
   const float* rg = p.right + (int64_t)g * P * p.ld_right;
   float* og = p.pooled + (int64_t)g * p.ld_pooled;
-  for (int d = tid; d < Dr; d += ATT_THREADS) {
-    float acc[ATT_MAX_HEADS];
+  const int dpad = (Dr + 31) & ~31;
+  const int parts = max(1, min(ATT_MAX_PARTS, min(ATT_THREADS / dpad, P)));
+  if (parts == 1) {
+    for (int d = tid; d < Dr; d += ATT_THREADS) {
+      float acc[ATT_MAX_HEADS];
 #pragma unroll
-    for (int c = 0; c < ATT_MAX_HEADS; ++c) acc[c] = 0.f;
-    for (int pp = 0; pp < P; ++pp) {
-      const float rv = __ldg(rg + (int64_t)pp * p.ld_right + d);
+      for (int c = 0; c < ATT_MAX_HEADS; ++c) acc[c] = 0.f;
+      for (int pp = 0; pp < P; ++pp) {
+        const float rv = __ldg(rg + (int64_t)pp * p.ld_right + d);
+#pragma unroll
+        for (int c = 0; c < ATT_MAX_HEADS; ++c)
+          if (c < C) acc[c] = fmaf(rv, sE[pp * C + c], acc[c]);
+      }
 #pragma unroll
       for (int c = 0; c < ATT_MAX_HEADS; ++c)
-        if (c < C) acc[c] = fmaf(rv, sE[pp * C + c], acc[c]);
+        if (c < C) og[(int64_t)d * C + c] = acc[c];
     }
+  } else {
+    float* sPart = sE + P * C;                       // [parts][Dr][C]
+    const int part = tid / dpad, d = tid % dpad;
+    if (part < parts && d < Dr) {
+      const int per = (P + parts - 1) / parts;
+      const int p0 = part * per, p1 = min(P, p0 + per);
+      float acc[ATT_MAX_HEADS];
 #pragma unroll
-    for (int c = 0; c < ATT_MAX_HEADS; ++c)
-      if (c < C) og[(int64_t)d * C + c] = acc[c];
+      for (int c = 0; c < ATT_MAX_HEADS; ++c) acc[c] = 0.f;
+      for (int pp = p0; pp < p1; ++pp) {
+        const float rv = __ldg(rg + (int64_t)pp * p.ld_right + d);
+#pragma unroll
+        for (int c = 0; c < ATT_MAX_HEADS; ++c)
+          if (c < C) acc[c] = fmaf(rv, sE[pp * C + c], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < ATT_MAX_HEADS; ++c)
+        if (c < C) sPart[((size_t)part * Dr + d) * C + c] = acc[c];
+    }
+    __syncthreads();
+    for (int q = tid; q < Dr * C; q += ATT_THREADS) {
+      float v = 0.f;
+      for (int part2 = 0; part2 < parts; ++part2) v += sPart[(size_t)part2 * Dr * C + q];   // fixed order: deterministic
+      og[q] = v;
+    }
   }
 }
 
-// bwd smem: W2 (C*H) | dO (Dr*C) | att (P*C) | de (P*C) | dot (C)
+// bwd smem: W2 (C*H) | dO (Dr*C) | att (P*C) | de (P*C) | dot (C) | du_sum partials (parts*H)
 __global__ void __launch_bounds__(ATT_THREADS) att_pool_bwd_kernel(const __grid_constant__ AttParams p) {
   extern __shared__ __align__(16) float smem[];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -154,22 +184,39 @@ __global__ void __launch_bounds__(ATT_THREADS) att_pool_bwd_kernel(const __grid_
   // du[p,h] = (de[p,:] @ W2[:,h]) * (1 - t^2);  du_sum[h] = sum_p du[p,h]
   const float* tg = p.t + (int64_t)g * P * H;
   float* dug = p.du + (int64_t)g * P * H;
-  for (int h = tid; h < H; h += ATT_THREADS) {
-    float w[ATT_MAX_HEADS];
+  {
+    const int hpad = (H + 31) & ~31;
+    const int parts = max(1, min(ATT_MAX_PARTS, min(ATT_THREADS / hpad, P)));
+    float* sSum = sDot + C;                          // [parts][H] partial du_sum
+    const int per = (P + parts - 1) / parts;
+    for (int idx = tid; idx < parts * hpad; idx += ATT_THREADS) {
+      const int part = idx / hpad, h = idx % hpad;
+      if (h >= H) continue;
+      float w[ATT_MAX_HEADS];
 #pragma unroll
-    for (int c = 0; c < ATT_MAX_HEADS; ++c) w[c] = c < C ? sW2[c * H + h] : 0.f;
-    float sum = 0.f;
-    for (int pp = 0; pp < P; ++pp) {
-      float dt = 0.f;
+      for (int c = 0; c < ATT_MAX_HEADS; ++c) w[c] = c < C ? sW2[c * H + h] : 0.f;
+      float sum = 0.f;
+      const int p0 = part * per, p1 = min(P, p0 + per);
+      for (int pp = p0; pp < p1; ++pp) {
+        float dt = 0.f;
 #pragma unroll
-      for (int c = 0; c < ATT_MAX_HEADS; ++c)
-        if (c < C) dt = fmaf(sDe[pp * C + c], w[c], dt);
-      const float tv = __ldg(tg + (int64_t)pp * H + h);
-      const float duv = dt * (1.0f - tv * tv);
-      dug[(int64_t)pp * H + h] = duv;
-      sum += duv;
+        for (int c = 0; c < ATT_MAX_HEADS; ++c)
+          if (c < C) dt = fmaf(sDe[pp * C + c], w[c], dt);
+        const float tv = __ldg(tg + (int64_t)pp * H + h);
+        const float duv = dt * (1.0f - tv * tv);
+        dug[(int64_t)pp * H + h] = duv;
+        sum += duv;
+      }
+      sSum[part * H + h] = sum;
     }
-    if (p.du_sum) p.du_sum[(int64_t)g * H + h] = sum;
+    __syncthreads();
+    if (p.du_sum) {
+      for (int h = tid; h < H; h += ATT_THREADS) {
+        float v = 0.f;
+        for (int part = 0; part < parts; ++part) v += sSum[part * H + h];
+        p.du_sum[(int64_t)g * H + h] = v;
+      }
+    }
   }
   // dright[p,d] (+)= sum_c att[p,c] * dO[d,c]
   float* drg = p.dright + (int64_t)g * P * p.ld_dright;
@@ -204,7 +251,7 @@ extern "C" int get_att_pool_fwd_f32(const float* t, const float* right, int64_t 
   memset(&p, 0, sizeof(p));
   p.t = t; p.right = right; p.ld_right = ld_right; p.W2 = W2; p.mask = mask;
   p.G = G; p.P = P; p.H = H; p.Dr = Dr; p.C = C; p.att = att; p.pooled = pooled; p.ld_pooled = ld_pooled;
-  const size_t smem = ((size_t)C * H + (size_t)P * C) * sizeof(float);
+  const size_t smem = ((size_t)C * H + (size_t)P * C + (size_t)ATT_MAX_PARTS * Dr * C) * sizeof(float);
   GETB_REQUIRE(smem <= 200 * 1024, "get_att_pool_fwd_f32: shared memory %zu too large", smem);
   static bool attr_set = false;
   if (!attr_set) {
@@ -229,7 +276,7 @@ extern "C" int get_att_pool_bwd_f32(const float* t, const float* right, int64_t 
   p.d_pooled = d_pooled; p.ld_dpooled = ld_dpooled; p.d_att = d_att;
   p.G = G; p.P = P; p.H = H; p.Dr = Dr; p.C = C;
   p.de = de; p.du = du; p.du_sum = du_sum; p.dright = dright; p.ld_dright = ld_dright; p.accumulate = accumulate;
-  const size_t smem = ((size_t)C * H + (size_t)Dr * C + (size_t)2 * P * C + C) * sizeof(float);
+  const size_t smem = ((size_t)C * H + (size_t)Dr * C + (size_t)2 * P * C + C + (size_t)ATT_MAX_PARTS * H) * sizeof(float);
   GETB_REQUIRE(smem <= 200 * 1024, "get_att_pool_bwd_f32: shared memory %zu too large", smem);
   static bool attr_set = false;
   if (!attr_set) {

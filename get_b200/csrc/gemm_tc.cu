@@ -313,7 +313,25 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   const float x = src[(int64_t)r * ld_r + (int64_t)c * ld_c];
   const float h = __uint_as_float(f32_to_tf32_rn(x));
   hi[(int64_t)r * ld_out + c] = h;
-  lo[(int64_t)r * ld_out + c] = x - h;
+  lo[(int64_t)r * ld_out + c] = __uint_as_float(f32_to_tf32_rn(x - h));
+}
+
+// every cached weight of the model in ONE launch: block -> job by binary search over the jobs' first blocks
+__global__ void __launch_bounds__(256) split_tf32_multi_kernel(const get_split_job* __restrict__ jobs, int n_jobs) {
+  int lo_j = 0, hi_j = n_jobs - 1;
+  const int64_t b = blockIdx.x;
+  while (lo_j < hi_j) {
+    const int mid = (lo_j + hi_j + 1) >> 1;
+    if (jobs[mid].first_block <= b) lo_j = mid; else hi_j = mid - 1;
+  }
+  const get_split_job j = jobs[lo_j];
+  const int64_t i = (b - j.first_block) * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)j.rows * j.cols) return;
+  const int r = (int)(i / j.cols), c = (int)(i % j.cols);
+  const float x = j.src[(int64_t)r * j.ld_r + (int64_t)c * j.ld_c];
+  const float h = __uint_as_float(f32_to_tf32_rn(x));
+  j.hi[(int64_t)r * j.ld_out + c] = h;
+  j.lo[(int64_t)r * j.ld_out + c] = __uint_as_float(f32_to_tf32_rn(x - h));
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -455,5 +473,12 @@ extern "C" int get_split_tf32_f32(const float* src, int64_t ld_r, int64_t ld_c, 
   const int64_t n = (int64_t)rows * cols;
   split_tf32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld_r, ld_c, rows, cols, hi, lo, ld_out);
   GETB_CHECK_LAUNCH("get_split_tf32_f32");
+  return 0;
+}
+
+extern "C" int get_split_tf32_multi_f32(const get_split_job* jobs_dev, int n_jobs, int64_t total_blocks, void* stream) {
+  GETB_REQUIRE(jobs_dev && n_jobs > 0 && total_blocks > 0 && total_blocks < 2147483647, "get_split_tf32_multi_f32: bad arguments");
+  split_tf32_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, n_jobs);
+  GETB_CHECK_LAUNCH("get_split_tf32_multi_f32");
   return 0;
 }

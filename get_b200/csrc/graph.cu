@@ -15,6 +15,8 @@
 //    shuffles; every HBM byte of the graph is read exactly once and every output row written once, coalesced.
 //  * graph_kernel (generic fallback, any N/H/alignment): adjacency in shared memory when it fits, feature rows
 //    streamed through L2 with 128-bit loads.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace getb {
@@ -485,6 +487,287 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
   }
 }
 
+// =====================================================================================================
+// Cluster path (experimental, opt-in): one graph per 2-CTA thread-block cluster, each CTA owns half of the feature
+// columns. Two such CTAs (~103 KB of shared memory, 512 threads) are co-resident per SM, so one CTA's TMA loads overlap
+// the other's compute, and a 216-graph launch becomes 432 half-size work items instead of two partial waves.
+// The only cross-CTA data are the N partial scorer dot products, exchanged through distributed shared memory.
+// Measured on B200: 37 us vs 35 us at 216 graphs and 928 us vs 566 us at 7 680 graphs -- the duplicated list building /
+// top-k and the 38-of-64 lane utilisation of the half rows cost more than the overlap buys, so it is not the default.
+// =====================================================================================================
+constexpr int GC_THREADS = 512;
+constexpr int GC_WARPS = GC_THREADS / 32;
+constexpr int GC_ROWS_PER_WARP = GS_MAX_N / GC_WARPS;   // 8
+
+__device__ __forceinline__ uint32_t gc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float gc_ld_peer(const float* local_ptr, uint32_t peer) {
+  uint32_t raddr;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(gs_smem_u32(local_ptr)), "r"(peer));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
+}
+
+// smem: [F N*WP f32 (own columns, row pitch WP)] [adj N*N f32 -> per-row lists in place, N/2 entries of 8 B per row]
+//       [part N] [sp N] [score N] [cnt N i32] [rank N i32] [keep N u8] [mbarriers 1 + GS_CHUNKS]
+template <bool FUSED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GC_THREADS, 2) graph_cluster_kernel(const __grid_constant__ GraphParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int g = blockIdx.x >> 1;
+  const uint32_t crank = gc_cluster_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, H = p.H, HQ = H >> 2;
+  const int qsplit = (HQ + 1) >> 1;                 // quads of rank 0; rank 1 owns the rest
+  const int q0 = crank ? qsplit : 0;                // first global quad of this CTA
+  const int WQ = crank ? HQ - qsplit : qsplit;      // quads owned
+  const int WP = qsplit * 4;                        // smem row pitch in floats (same for both ranks)
+  const uint32_t salt = (FUSED && p.thr) ? __ldg(p.salt) : 0u;
+  const uint32_t seed_s = p.seed_s + salt, seed_2 = p.seed_2 + salt;
+
+  float* sF = smem;
+  float* sA = sF + (size_t)N * WP;
+  float* s_part = sA + (size_t)N * N;
+  float* s_sp = s_part + N;
+  float* s_score = s_sp + N;
+  int* s_cnt = reinterpret_cast<int*>(s_score + N);
+  int* s_rank = s_cnt + N;
+  uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_rank + N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_keep + ((N + 15) & ~15));
+
+  const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
+  const float* __restrict__ gx = p.x + (int64_t)g * N * H + (int64_t)q0 * 4;
+  float* __restrict__ gout = p.out + (int64_t)g * N * H + (int64_t)q0 * 4;
+  const int nchunks = (N + 31) >> 5;
+  const bool own0 = lane < WQ, own1 = lane + 32 < WQ;   // this lane's (up to two) quads of a row
+
+  if (tid == 0) {
+    for (int b = 0; b <= GS_CHUNKS; ++b) gs_mbar_init(&bars[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t abytes = (uint32_t)N * (uint32_t)N * 4u;
+      gs_mbar_expect_tx(&bars[0], abytes);
+      gs_bulk_g2s(sA, gadj, abytes, &bars[0]);
+    }
+    const uint32_t rowbytes = (uint32_t)WQ * 16u;
+    for (int c = 0; c < nchunks; ++c) {
+      const int r0 = c * 32, nr = min(N, r0 + 32) - r0;
+      if (lane == 0) gs_mbar_expect_tx(&bars[1 + c], (uint32_t)nr * rowbytes);
+      __syncwarp();
+      if (lane < nr) gs_bulk_g2s(sF + (size_t)(r0 + lane) * WP, gx + (size_t)(r0 + lane) * H, rowbytes, &bars[1 + c]);
+    }
+  }
+  if (tid < N) {
+    s_rank[tid] = 0;
+    if (!FUSED) s_keep[tid] = p.keep_in ? p.keep_in[(int64_t)g * N + tid] : (uint8_t)1;
+  }
+
+  // ---- neighbour lists in place: row i -> {byte offset of F row j, w_ij}; rows with more than N/2 neighbours stay dense
+  gs_mbar_wait(&bars[0], 0);
+  {
+    float wv[GC_ROWS_PER_WARP][4];
+#pragma unroll
+    for (int r = 0; r < GC_ROWS_PER_WARP; ++r) {
+      const int i = warp + r * GC_WARPS;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = c * 32 + lane;
+        wv[r][c] = (i < N && j < N) ? (p.transpose ? sA[(size_t)j * N + i] : sA[(size_t)i * N + j]) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < GC_ROWS_PER_WARP; ++r) {
+      const int i = warp + r * GC_WARPS;
+      if (i < N) {
+        unsigned nz[4];
+        int total = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          nz[c] = __ballot_sync(0xffffffffu, wv[r][c] != 0.f);
+          total += __popc(nz[c]);
+        }
+        if (total <= N / 2) {
+          float2* lr = reinterpret_cast<float2*>(sA + (size_t)i * N);
+          int pos = 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (wv[r][c] != 0.f)
+              lr[pos + __popc(nz[c] & ((1u << lane) - 1u))] = make_float2(__int_as_float((c * 32 + lane) * WP * 4), wv[r][c]);
+            pos += __popc(nz[c]);
+          }
+          if (lane == 0) s_cnt[i] = total;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {     // dense row of op(adj) (matters for transpose); aggregated by column scan
+            const int j = c * 32 + lane;
+            if (j < N) sA[(size_t)i * N + j] = wv[r][c];
+          }
+          if (lane == 0) s_cnt[i] = -1;
+        }
+      }
+    }
+  }
+
+  if (FUSED) {
+    // ---- partial s_p over the own columns; layer-2 dropout applied in place on the way -------------------------
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+    if (own0) w0 = __ldg(reinterpret_cast<const float4*>(p.wp) + q0 + lane);
+    if (own1) w1 = __ldg(reinterpret_cast<const float4*>(p.wp) + q0 + lane + 32);
+    for (int c = 0; c < nchunks; ++c) {
+      gs_mbar_wait(&bars[1 + c], 0);
+      for (int i = c * 32 + warp; i < min(N, c * 32 + 32); i += GC_WARPS) {
+        float4* row = reinterpret_cast<float4*>(sF + (size_t)i * WP) + lane;
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 0 ? own0 : own1) {
+            float4 f = row[u * 32];
+            if (p.thr) {
+              const uint64_t base = ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)(q0 + lane + u * 32) * 4;
+              float4 f2 = f;
+              drop_apply4(seed_2, base, p.thr, p.scale, f2);
+              row[u * 32] = f2;
+              drop_apply4(seed_s, base, p.thr, p.scale, f);
+            }
+            const float4 w = u == 0 ? w0 : w1;
+            acc = fmaf(f.x, w.x, acc); acc = fmaf(f.y, w.y, acc);
+            acc = fmaf(f.z, w.z, acc); acc = fmaf(f.w, w.w, acc);
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_part[i] = acc;
+      }
+    }
+    __syncthreads();
+    gc_cluster_arrive();
+    gc_cluster_wait();                      // both halves of every dot product are in place
+    if (tid < N) {
+      const float mine = s_part[tid], peer = gc_ld_peer(&s_part[tid], crank ^ 1u);
+      s_sp[tid] = crank ? peer + mine : mine + peer;      // rank-0 half first in both CTAs: identical bits
+    }
+    gc_cluster_arrive();                    // (second phase) waited for at the very end: the peer may still be reading
+    __syncthreads();
+    // ---- s_a = adj @ s_p + scalar GRU gates (GGNN with out_features = 1), one thread per node ----------------
+    if (tid < N) {
+      const int i = tid;
+      const int cnt = s_cnt[i];
+      const float inv_rowbytes = 1.0f / (float)(WP * 4);
+      float sa = 0.f;
+      if (cnt >= 0) {
+        const float2* lr = reinterpret_cast<const float2*>(sA + (size_t)i * N);
+        for (int e = 0; e < cnt; ++e) {
+          const float2 en = lr[e];
+          sa = fmaf(en.y, s_sp[__float2int_rn(__int2float_rn(__float_as_int(en.x)) * inv_rowbytes)], sa);
+        }
+      } else {
+        for (int j = 0; j < N; ++j) sa = fmaf(sA[(size_t)i * N + j], s_sp[j], sa);
+      }
+      const float wz0 = __ldg(p.gate + 0), bz0 = __ldg(p.gate + 1), wz1 = __ldg(p.gate + 2), bz1 = __ldg(p.gate + 3);
+      const float wr0 = __ldg(p.gate + 4), br0 = __ldg(p.gate + 5), wr1 = __ldg(p.gate + 6), br1 = __ldg(p.gate + 7);
+      const float wh0 = __ldg(p.gate + 8), bh0 = __ldg(p.gate + 9), wh1 = __ldg(p.gate + 10), bh1 = __ldg(p.gate + 11);
+      const float sp = s_sp[i];
+      const float z = sigmoidf_((wz0 * sa + bz0) + (wz1 * sp + bz1));
+      const float r = sigmoidf_((wr0 * sa + br0) + (wr1 * sp + br1));
+      const float h = tanhf((wh0 * sa + bh0) + (wh1 * (r * sp) + bh1));
+      const float sc = h * z + sp * (1.0f - z);
+      s_score[i] = sc;
+      if (p.score && crank == 0) p.score[(int64_t)g * N + i] = sc;
+    }
+    __syncthreads();
+    {
+      const int i = tid & (GS_MAX_N - 1);
+      const int j0 = (tid >> 7) * 32;         // 4 slices of 32 candidates
+      if (i < N && j0 < N) {
+        const float si = s_score[i];
+        const int j1 = min(N, j0 + 32);
+        int rank = 0;
+        for (int j = j0; j < j1; ++j) {
+          const float sj = s_score[j];
+          rank += ((sj > si) || (sj == si && j < i)) ? 1 : 0;
+        }
+        if (rank) atomicAdd(&s_rank[i], rank);
+      }
+    }
+    __syncthreads();
+    if (tid < N) {
+      const uint8_t kp = s_rank[tid] < p.k;
+      s_keep[tid] = kp;
+      if (crank == 0) p.keep_out[(int64_t)g * N + tid] = kp;
+    }
+    __syncthreads();
+  } else {
+    for (int c = 0; c < nchunks; ++c) gs_mbar_wait(&bars[1 + c], 0);
+    __syncthreads();
+  }
+
+  // ---- out[i, own columns] = sum_e w[i][e] * x[idx[i][e], own columns] -----------------------------------------
+  const bool masked = FUSED || (p.keep_in != nullptr);
+  const char* sFb = reinterpret_cast<const char*>(sF) + lane * 16;
+  const float inv_rowbytes = 1.0f / (float)(WP * 4);
+  for (int i = warp; i < N; i += GC_WARPS) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    const int cnt = s_cnt[i];
+    const bool dropped = masked && s_keep[i] == 0;   // a dropped node keeps only its edges to kept nodes
+    if (cnt >= 0) {
+      float2* lr = reinterpret_cast<float2*>(sA + (size_t)i * N);
+      if (dropped) {
+        for (int e = lane; e < cnt; e += 32) {
+          const int j = __float2int_rn(__int2float_rn(__float_as_int(lr[e].x)) * inv_rowbytes);
+          if (!s_keep[j]) lr[e].y = 0.f;
+        }
+        __syncwarp();
+      }
+#pragma unroll 2
+      for (int e = 0; e < cnt; ++e) {
+        const float2 en = lr[e];
+        const float wj = en.y;
+        const float4* row = reinterpret_cast<const float4*>(sFb + __float_as_int(en.x));
+        if (own0) {
+          const float4 f = row[0];
+          a0.x = fmaf(wj, f.x, a0.x); a0.y = fmaf(wj, f.y, a0.y); a0.z = fmaf(wj, f.z, a0.z); a0.w = fmaf(wj, f.w, a0.w);
+        }
+        if (own1) {
+          const float4 f = row[32];
+          a1.x = fmaf(wj, f.x, a1.x); a1.y = fmaf(wj, f.y, a1.y); a1.z = fmaf(wj, f.z, a1.z); a1.w = fmaf(wj, f.w, a1.w);
+        }
+      }
+    } else {
+      for (int j = 0; j < N; ++j) {               // dense row (more than N/2 neighbours)
+        float wj = sA[(size_t)i * N + j];
+        if (wj == 0.f || (dropped && !s_keep[j])) continue;
+        const float4* row = reinterpret_cast<const float4*>(sFb + (size_t)j * WP * 4);
+        if (own0) {
+          const float4 f = row[0];
+          a0.x = fmaf(wj, f.x, a0.x); a0.y = fmaf(wj, f.y, a0.y); a0.z = fmaf(wj, f.z, a0.z); a0.w = fmaf(wj, f.w, a0.w);
+        }
+        if (own1) {
+          const float4 f = row[32];
+          a1.x = fmaf(wj, f.x, a1.x); a1.y = fmaf(wj, f.y, a1.y); a1.z = fmaf(wj, f.z, a1.z); a1.w = fmaf(wj, f.w, a1.w);
+        }
+      }
+    }
+    float4* orow = reinterpret_cast<float4*>(gout + (int64_t)i * H) + lane;
+    if (own0) {
+      if (p.accumulate) { const float4 o = orow[0]; a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w; }
+      orow[0] = a0;
+    }
+    if (own1) {
+      if (p.accumulate) { const float4 o = orow[32]; a1.x += o.x; a1.y += o.y; a1.z += o.z; a1.w += o.w; }
+      orow[32] = a1;
+    }
+  }
+  if (FUSED) gc_cluster_wait();   // the peer has finished reading this CTA's partial scores
+}
+
 typedef void (*GraphSmemFn)(const GraphParams);
 static GraphSmemFn graph_smem_fn(bool fused, int nq) {
   switch (nq) {
@@ -529,7 +812,36 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
   GETB_REQUIRE(p.H <= 32 * 4 * MAX_QUADS_PER_LANE, "%s: H=%d exceeds %d", name, p.H, 32 * 4 * MAX_QUADS_PER_LANE);
   if (p.G == 0) return 0;
   {
-    // fast path: the whole graph (features + adjacency) staged in shared memory by TMA bulk copies
+    // experimental path (GET_B200_GRAPH_CLUSTER=1): 2-CTA cluster per graph, feature columns split between the CTAs
+    const int hq = p.H / 4, wp = ((hq + 1) / 2) * 4;
+    const size_t need_c = ((size_t)p.N * wp + (size_t)p.N * p.N + 5 * (size_t)p.N) * sizeof(float) +
+                          (((size_t)p.N + 15) & ~(size_t)15) + (GS_CHUNKS + 1) * sizeof(uint64_t);
+    static int use_cluster = -1;
+    if (use_cluster < 0) {
+      const char* e = getenv("GET_B200_GRAPH_CLUSTER");
+      use_cluster = e ? atoi(e) : 0;   // measured slower than the single-CTA path on B200 (profiles/): opt-in only
+    }
+    const bool okc = use_cluster && (p.H % 4) == 0 && hq >= 2 && (hq + 1) / 2 <= 64 && (p.N % 2) == 0 && p.N <= GS_MAX_N &&
+                     aligned16(p.adj) && aligned16(p.x) && aligned16(p.out) && (!fused || aligned16(p.wp)) &&
+                     need_c <= GS_SMEM_LIMIT && p.G <= (1 << 29);
+    if (okc) {
+      void (*fn)(const GraphParams) = fused ? graph_cluster_kernel<true> : graph_cluster_kernel<false>;
+      static bool attr_c[2] = {false, false};
+      if (!attr_c[fused ? 1 : 0]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM_LIMIT) != cudaSuccess) {
+          set_error("%s: cannot opt in to %d bytes of shared memory", name, (int)GS_SMEM_LIMIT);
+          (void)cudaGetLastError();
+          return -2;
+        }
+        attr_c[fused ? 1 : 0] = true;
+      }
+      fn<<<2 * p.G, GC_THREADS, need_c, st>>>(p);
+      GETB_CHECK_LAUNCH(name);
+      return 0;
+    }
+  }
+  {
+    // single-CTA path: the whole graph (features + adjacency) staged in shared memory by TMA bulk copies
     const size_t need = ((size_t)p.N * p.H + 2 * (size_t)p.N * p.N + 4 * (size_t)p.N) * sizeof(float) +
                         (((size_t)p.N + 15) & ~(size_t)15) + (GS_CHUNKS + 1) * sizeof(uint64_t);
     const bool ok = (p.H % 4) == 0 && p.H <= 128 * GS_MAX_QUADS && (p.N % 2) == 0 && p.N <= GS_MAX_N && aligned16(p.adj) &&

@@ -53,13 +53,20 @@ class FlatGradAllReduce(object):
             off += p.numel()
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
 
+    def init_collective(self):
+        """One all-reduce of the (zero) bucket: creates the communicator outside of any stream capture. Every rank must
+        call it the same number of times."""
+        if self.world > 1:
+            dist.all_reduce(self.flat, group=self.group)
+
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * 4
 
-    def reduce(self, weight: float = 1.0):
+    def reduce(self, weight: float = 1.0, collective: bool = True):
         """Average gradients over ranks (each rank's loss is a mean over its local claims; `weight` =
-        local_claims * world / global_claims re-weights unequal shards). Leaves p.grad pointing into the bucket."""
+        local_claims * world / global_claims re-weights unequal shards). Leaves p.grad pointing into the bucket.
+        collective=False only gathers the gradients into the bucket (warm-up steps that must not talk to other ranks)."""
         grads, views = [], []
         for p, v in zip(self.params, self.views):
             if p.grad is None:
@@ -69,7 +76,7 @@ class FlatGradAllReduce(object):
                 views.append(v)
         if grads:
             torch._foreach_copy_(views, grads)
-        if self.world > 1:
+        if self.world > 1 and collective:
             if weight != 1.0:
                 self.flat.mul_(weight)
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM,

@@ -99,32 +99,77 @@ def begin_step_capture():
     _split_epoch += 1
 
 
+_split_table = None        # (device uint8 tensor holding get_split_job[], n_jobs, total_blocks, keys) or None when stale
+
+
+def _run_single_split(b, hi, lo):
+    lib = _lib.load()
+    N, K = b.shape
+    _lib.check(lib.get_split_tf32_f32(b.data_ptr(), b.stride(0), b.stride(1), N, K, hi.data_ptr(), lo.data_ptr(),
+                                      hi.stride(0), _stream()), "get_split_tf32_f32")
+
+
+def prepare_split_table():
+    """(Re)build the device job table covering every cached weight. Copies host memory to the device, so it must run
+    OUTSIDE a stream capture (CapturedTrainStep calls it right before capturing)."""
+    global _split_table
+    if _split_table is not None or not _split_cache:
+        return
+    keys = list(_split_cache.keys())
+    jobs = (_lib.SplitJob * len(keys))()
+    blocks = 0
+    for j, key in enumerate(keys):
+        ent = _split_cache[key]
+        ptr, shape, strides = key
+        jobs[j].src, jobs[j].ld_r, jobs[j].ld_c = ptr, strides[0], strides[1]
+        jobs[j].rows, jobs[j].cols = shape
+        jobs[j].hi, jobs[j].lo, jobs[j].ld_out = ent[1].data_ptr(), ent[2].data_ptr(), ent[1].stride(0)
+        jobs[j].first_block = blocks
+        blocks += (shape[0] * shape[1] + 255) // 256
+    raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+    _split_table = (raw.to(ent[1].device), len(keys), blocks, keys)
+
+
 def split_weight(b: torch.Tensor):
     """(hi, lo) k-contiguous TF32 split of a weight view b (logical (N, K), any strides), cached per
-    (storage address, shape, strides) and refreshed when the parameter's version counter moves (optimizer step) or a
-    captured step begins (begin_step_capture)."""
+    (storage address, shape, strides). Refreshed when the weights change: the optimizer post-step hook / a captured step
+    bump the epoch and the FIRST weight asked for afterwards refreshes every cached split in one launch; a moved version
+    counter (in-place edit of one tensor) refreshes that tensor alone."""
+    global _split_table
     key = (b.data_ptr(), tuple(b.shape), tuple(b.stride()))
     ent = _split_cache.get(key)
-    ver = (b._version, _split_epoch)
-    if ent is not None and ent[0] == ver:
+    if ent is not None and ent[0] == (b._version, _split_epoch):
         return ent[1], ent[2]
-    lib = _lib.load()
     _chk_f32(b, "B")
-    N, K = b.shape
-    ldo = (K + 3) // 4 * 4
-    if ent is not None:
-        hi, lo = ent[1], ent[2]
-    else:
+    if ent is None:
+        N, K = b.shape
+        ldo = (K + 3) // 4 * 4
         hi = torch.zeros((N, ldo), dtype=torch.float32, device=b.device)
         lo = torch.zeros((N, ldo), dtype=torch.float32, device=b.device)
-    _lib.check(lib.get_split_tf32_f32(b.data_ptr(), b.stride(0), b.stride(1), N, K, hi.data_ptr(), lo.data_ptr(), ldo,
-                                      _stream()), "get_split_tf32_f32")
-    # the entry pins the source storage: while it is cached the allocator cannot hand the same address to another
-    # tensor, so (address, shape, strides, version) identifies the weight values exactly
-    _split_cache[key] = (ver, hi, lo, b.untyped_storage())
-    if len(_split_cache) > _SPLIT_CACHE_MAX:
-        _split_cache.pop(next(iter(_split_cache)))
-    return hi, lo
+        _run_single_split(b, hi, lo)
+        # the entry pins the source storage: while it is cached the allocator cannot hand the same address to another
+        # tensor, so (address, shape, strides) identifies the weight
+        _split_cache[key] = [(b._version, _split_epoch), hi, lo, b.untyped_storage()]
+        if len(_split_cache) > _SPLIT_CACHE_MAX:
+            _split_cache.pop(next(iter(_split_cache)))
+        _split_table = None              # the job table no longer matches the cache
+        return hi, lo
+    if ent[0][1] != _split_epoch:
+        capturing = torch.cuda.is_current_stream_capturing()
+        if _split_table is None and not capturing:
+            prepare_split_table()
+        if _split_table is not None:
+            tab, n, blocks, keys = _split_table
+            _lib.check(_lib.load().get_split_tf32_multi_f32(tab.data_ptr(), n, blocks, _stream()), "get_split_tf32_multi_f32")
+            for k2 in keys:
+                e2 = _split_cache.get(k2)
+                if e2 is not None:
+                    e2[0] = (e2[0][0], _split_epoch)
+            if ent[0][0] == b._version:
+                return ent[1], ent[2]
+    _run_single_split(b, ent[1], ent[2])
+    ent[0] = (b._version, _split_epoch)
+    return ent[1], ent[2]
 
 
 def dropout_salt_set(value: int):

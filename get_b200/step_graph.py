@@ -80,13 +80,20 @@ class CapturedTrainStep(object):
     """step(query, document, labels, kwargs, n_real_claims) -> loss (0-d device tensor, valid until the next step).
 
     All tensor arguments may live on the host (pinned for asynchronous copies) or on the device; shapes select the graph.
-    `optimizer` (capturable) and `reducer` (get_b200.ddp.FlatGradAllReduce) are optional parts of the captured step."""
+    `optimizer` (capturable) and `reducer` (get_b200.ddp.FlatGradAllReduce) are optional parts of the captured step.
+    Multi-GPU: every call of step() executes exactly one gradient all-reduce (inside the replayed graph), whether or not
+    the shape is new on this rank, so ranks stay in lock-step as long as they call step() equally often."""
 
-    def __init__(self, model, optimizer=None, reducer=None, loss_fn=None):
+    def __init__(self, model, optimizer=None, reducer=None, loss_fn=None, collective_in_graph: bool = True):
         self.model, self.optimizer, self.reducer = model, optimizer, reducer
+        # collective_in_graph=False: the graph ends after the backward pass (gradients gathered in the flat bucket); the
+        # all-reduce and the optimizer step are then issued eagerly after every replay
+        self.split_tail = (not collective_in_graph) and reducer is not None and reducer.world > 1
         self.loss_fn = loss_fn or ops.cross_entropy
         self.slots: Dict[Tuple, _Slot] = {}
         self.device = next(model.parameters()).device
+        if reducer is not None:
+            reducer.init_collective()    # communicator created here, never inside a capture
         self.replayed_launches = 0       # kernels of libget_b200.so launched through graph replays so far
 
     # ---------------------------------------------------------------------------------------------------------
@@ -94,15 +101,21 @@ class CapturedTrainStep(object):
         return (tuple(query.shape), tuple(document.shape), tuple(kw[K.DocContentNoPaddingEvidence].shape),
                 tuple(kw[K.Evd_Docs_Adj].shape), str(kw[K.Evd_Docs_Adj].dtype), int(n_real), bool(self.model.training))
 
-    def _eager(self, s: _Slot):
+    def _eager(self, s: _Slot, collective: bool = True):
         logits = self.model(s.query, s.document, **s.kw)
         loss = self.loss_fn(logits[:s.n_real], s.labels[:s.n_real])
         loss.backward()
         if self.reducer is not None:
-            self.reducer.reduce()
-        if self.optimizer is not None:
+            self.reducer.reduce(collective=collective and not self.split_tail)
+        if self.optimizer is not None and not self.split_tail:
             self.optimizer.step()
         return logits, loss
+
+    def _tail(self):
+        """all-reduce + optimizer step outside the graph (collective_in_graph=False)."""
+        self.reducer.reduce(collective=True)
+        if self.optimizer is not None:
+            self.optimizer.step()
 
     def _build(self, query, document, labels, kw, n_real) -> _Slot:
         dev = self.device
@@ -134,7 +147,7 @@ class CapturedTrainStep(object):
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             self._zero_grad()
-            self._eager(s)
+            self._eager(s, collective=False)    # ranks see different shapes: building a graph must not be a collective
         cur.wait_stream(side)
         torch.cuda.synchronize()
         with torch.no_grad():
@@ -154,6 +167,7 @@ class CapturedTrainStep(object):
                             st[k] = old[k]
         ops.dropout_salt_set(salt)
         # ---- capture
+        ops.prepare_split_table()      # host -> device copy of the weight-split job table: not allowed inside the capture
         self._zero_grad()
         prof, ops.PROFILE_GSL_EVENTS = ops.PROFILE_GSL_EVENTS, None
         g = torch.cuda.CUDAGraph()
@@ -196,6 +210,8 @@ class CapturedTrainStep(object):
             self._copy_in(s, query, document, labels, kw)
         s.graph.replay()
         self.replayed_launches += s.launches
+        if self.split_tail:
+            self._tail()
         return s.loss
 
     @property

@@ -114,11 +114,22 @@ int get_gemm_f32(const get_gemm_desc* desc, void* stream);
 int get_gemm_f32_uses_tc(const get_gemm_desc* desc);
 
 /* Error-compensated TF32 split of a weight matrix for the tensor-core path:
- * hi = tf32_round_nearest(src), lo = src - hi. src is a logical (rows, cols) matrix addressed as
+ * hi = tf32_round_nearest(src), lo = tf32_round_nearest(src - hi). src is a logical (rows, cols) matrix addressed as
  * src[r*ld_r + c*ld_c] (so a transposed view can be split into a k-contiguous copy); hi/lo are (rows, cols)
  * row-major with leading dimension ld_out. */
 int get_split_tf32_f32(const float* src, int64_t ld_r, int64_t ld_c, int rows, int cols,
                        float* hi, float* lo, int64_t ld_out, void* stream);
+
+/* The same split for MANY matrices in one launch (all weights of the model once per optimizer step). `jobs` is an array
+ * in DEVICE memory; job j covers blocks [first_block, first_block + ceil(rows*cols/256)) of the launch, first_block
+ * ascending from 0; total_blocks = sum over jobs. */
+typedef struct get_split_job {
+  const float* src; int64_t ld_r, ld_c;
+  int32_t rows, cols;
+  float* hi; float* lo; int64_t ld_out;
+  int64_t first_block;
+} get_split_job;
+int get_split_tf32_multi_f32(const get_split_job* jobs, int n_jobs, int64_t total_blocks, void* stream);
 
 /* Number of kernels get_gemm_f32 will launch for this descriptor (1, or 2 with split-K). */
 int get_gemm_f32_launches(const get_gemm_desc* desc);
