@@ -186,9 +186,13 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
   __shared__ __align__(8) uint64_t bar_accf[2];                // accumulator set complete (tcgen05.commit)
   __shared__ __align__(8) uint64_t bar_acce[2];                // accumulator set drained (all epilogue threads arrive)
   __shared__ uint32_t tmem_holder;
-  __shared__ long long dbg_ts[4][24];   // GET_B200_T2_DEBUG=9: per-role timeline of CTA 0
+#ifdef GETB_T2_TIMELINE   // compile with -DGETB_T2_TIMELINE and run with GET_B200_T2_DEBUG=9: per-role timeline of CTA 0
+  __shared__ long long dbg_ts[4][24];
   const long long dbg_t0 = clock64();
 #define T2_DBG(role, idx) do { if (cfg.debug == 9 && blockIdx.x == 0 && (idx) < 24) dbg_ts[role][idx] = clock64() - dbg_t0; } while (0)
+#else
+#define T2_DBG(role, idx) do { } while (0)
+#endif
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = cfg.BN;
@@ -238,6 +242,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           t2_locate(cfg, p.nseg, kb, seg, kin);
           mbar_wait(&bar_empty[stage], phase ^ 1);
           if (kb == kb0) T2_DBG(0, it * 2); if (kb == kb1 - 1) T2_DBG(0, it * 2 + 1);
+          if (it == 0 && kb - kb0 >= 4 && kb - kb0 < 7) T2_DBG(0, 8 + (kb - kb0 - 4));
           const uint32_t sa = smem_base + (uint32_t)stage * cfg.stage_bytes;
           const uint32_t sbh = sa + cfg.a_stage, sbl = sbh + cfg.b_tile;
           mbar_arrive_expect_tx(&bar_raw[stage], tx);
@@ -285,6 +290,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           mbar_wait(&bar_ready[stage], phase);
           tc_fence_after();
           if (kb == kb0) T2_DBG(1, it * 3 + 1);
+          if (it == 0 && kb - kb0 >= 4 && kb - kb0 < 7) T2_DBG(1, 12 + (kb - kb0 - 4) * 2);
           const uint32_t a_hi = smem_base + (uint32_t)stage * cfg.stage_bytes;
           const uint32_t a_lo = a_hi + T2_A_TILE;
           const uint32_t b_hi = a_hi + cfg.a_stage;
@@ -317,6 +323,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           }
           }
           umma_commit(&bar_empty[stage]);
+          if (it == 0 && kb - kb0 >= 4 && kb - kb0 < 7) T2_DBG(1, 13 + (kb - kb0 - 4) * 2);
           if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_accf[acc]);
@@ -344,6 +351,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&bar_raw[stage], phase);
         if (t == 0 && kb == kb0) T2_DBG(3, it * 2); if (t == 0 && kb == kb1 - 1) T2_DBG(3, it * 2 + 1);
+        if (t == 0 && it == 0 && kb - kb0 >= 4 && kb - kb0 < 7) T2_DBG(3, 8 + (kb - kb0 - 4) * 4);
         const uint32_t a_hi = smem_base + (uint32_t)stage * cfg.stage_bytes;
         const uint32_t a_lo = a_hi + T2_A_TILE;
         if (cfg.a_tmem) {
@@ -398,7 +406,9 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
             sts128(b_lo + off, lo);
           }
         }
+        if (t == 0 && it == 0 && kb - kb0 >= 4 && kb - kb0 < 7) T2_DBG(3, 9 + (kb - kb0 - 4) * 4);
         fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+        if (t == 0 && it == 0 && kb - kb0 >= 4 && kb - kb0 < 7) T2_DBG(3, 10 + (kb - kb0 - 4) * 4);
         mbar_arrive(&bar_ready[stage]);
         if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
       }
@@ -513,13 +523,18 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
   }
   tc_fence_before();
   __syncthreads();
+#ifdef GETB_T2_TIMELINE
   if (cfg.debug == 9 && blockIdx.x == 0 && tid == 0) {
     for (int it = 0; it < n_my && it < 4; ++it)
       printf("T2DBG it=%d prod[%lld %lld] split[%lld %lld] mma[acce %lld ready %lld commit %lld] epi[%lld %lld]\n", it,
              dbg_ts[0][it * 2], dbg_ts[0][it * 2 + 1], dbg_ts[3][it * 2], dbg_ts[3][it * 2 + 1], dbg_ts[1][it * 3], dbg_ts[1][it * 3 + 1],
              dbg_ts[1][it * 3 + 2], dbg_ts[2][it * 2], dbg_ts[2][it * 2 + 1]);
+    for (int j = 0; j < 3; ++j)
+      printf("T2DBG kb=%d tma_issue %lld | split: raw_seen %lld stored %lld fenced %lld | mma: ready_seen %lld issued+commit %lld\n", 4 + j,
+             dbg_ts[0][8 + j], dbg_ts[3][8 + j * 4], dbg_ts[3][9 + j * 4], dbg_ts[3][10 + j * 4], dbg_ts[1][12 + j * 2], dbg_ts[1][13 + j * 2]);
     printf("T2DBG end %lld\n", clock64() - dbg_t0);
   }
+#endif
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg.tmem_cols) : "memory");
