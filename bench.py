@@ -330,8 +330,9 @@ def run_ours(args):
     #      replay), CUDA events on the launch stream around every get_gsl_fused_f32 launch ------------------------------
     gsl_ms, gsl_pairs, stream_roof = [], [], None
     if rank == 0:
-        ops.PROFILE_GSL_EVENTS = []
-        for i in range(min(args.steps, 16)):
+        # (1) the same steps issued kernel by kernel, recording the arguments of every fused GSL launch
+        ops.PROFILE_GSL_ARGS = []
+        for i in range(min(args.steps, NBATCH)):
             b = (i + args.warmup) % NBATCH
             q, d, l, kw = resident[b]
             opt.zero_grad(set_to_none=True)
@@ -339,9 +340,19 @@ def run_ours(args):
             loss.backward()
             opt.step()
         torch.cuda.synchronize()
-        gsl_events, ops.PROFILE_GSL_EVENTS = ops.PROFILE_GSL_EVENTS, None
-        gsl_ms = [a.elapsed_time(b) for a, b, _ in gsl_events]
-        gsl_pairs = [n for _, _, n in gsl_events]
+        recs, ops.PROFILE_GSL_ARGS = ops.PROFILE_GSL_ARGS, None
+        # (2) exactly those launches (same adjacency / layer-1 features / dropout seeds, ~60 MB of distinct inputs each,
+        #     ~1 GB in total > L2) replayed back to back between two events: the GPU never waits for the host, so the
+        #     event interval is kernel time. Three passes, the first is a warm-up.
+        for rep in range(3):
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_a.record()
+            npairs = [ops.gsl_fused_replay(r) for r in recs]
+            e_b.record()
+            torch.cuda.synchronize()
+            if rep > 0:
+                gsl_ms.append(e_a.elapsed_time(e_b) / len(recs))
+                gsl_pairs.append(float(np.mean(npairs)))
         stream_roof = stream_roofline(w, dev)
     barrier()
 
@@ -381,7 +392,8 @@ def run_ours(args):
             "e2e": {"value": pairs_e2e / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "graph_kernel<FUSED> (get_gsl_fused_f32)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "graph_smem_kernel<FUSED=1> (get_gsl_fused_f32), train-mode dropout, the bench batches' own launches replayed back to back",
+                         "bound": "hbm", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "avg_launch_ms": gsl_avg_ms, "algorithmic_bytes_per_launch": gsl_bytes,

@@ -19,6 +19,9 @@ _SM_COUNT = 148
 # bench.py sets this to a list to time the fused GSL kernel with CUDA events on its launch stream:
 # entries are (start_event, stop_event, n_graphs)
 PROFILE_GSL_EVENTS = None
+# bench.py sets this to a list to record the exact arguments of every fused GSL launch of a step (tensors kept alive) so
+# that the very same launches can be replayed back to back under CUDA events (gsl_fused_replay)
+PROFILE_GSL_ARGS = None
 
 
 def _stream() -> int:
@@ -300,6 +303,9 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     score = torch.empty((G, N), dtype=torch.float32, device=feat.device) if want_score else None
     keep = torch.empty((G, N), dtype=torch.uint8, device=feat.device)
     out = torch.empty_like(feat)
+    if PROFILE_GSL_ARGS is not None:
+        PROFILE_GSL_ARGS.append((adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF,
+                                 seed_layer2 & 0xFFFFFFFF, score, keep, out))
     prof = PROFILE_GSL_EVENTS
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -311,6 +317,16 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
         e1.record()
         prof.append((e0, e1, G))
     return score, keep, out
+
+
+def gsl_fused_replay(rec):
+    """Re-issue one recorded fused GSL launch (PROFILE_GSL_ARGS entry) with the same inputs and output buffers."""
+    adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out = rec
+    G, N, H = feat.shape
+    _lib.check(_lib.load().get_gsl_fused_f32(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k,
+                                             drop_p, s1, s2, _ptr(score), keep.data_ptr(), out.data_ptr(), _stream()),
+               "get_gsl_fused_f32")
+    return G
 
 
 def gsl_mask_adj(adj, score, k):

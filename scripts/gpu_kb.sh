@@ -1,4 +1,5 @@
 #!/bin/bash
 OUT=gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:gemm_tc2_kernel --csv --log-file $OUT/t_nt.csv python scripts/kbench.py gemm --M 21600 --N 300 --K 300 --seg 2 --iters 3 > /dev/null 2>&1
-grep gemm_tc2 $OUT/t_nt.csv | awk -F'","' '{print $NF}' | tr -d '"' | head -56 | tr '\n' ' '; echo
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_r1c.csv \
+    python bench.py --no-graph --steps 2 --warmup 3 > $OUT/ncu_launch_r1c.log 2>&1
+tail -1 $OUT/ncu_launch_r1c.log | cut -c1-200
