@@ -315,9 +315,19 @@ def run_ours(args):
     t0 = time.perf_counter()
     e2.record()
     pairs_e2e, h2d, d2h = 0, 0, 0
+    nxt = None
+    if use_graph:                                   # the next batch's H2D copy overlaps the current step (side stream)
+        b0 = args.warmup % NBATCH
+        nxt = stepper.prefetch(*host[b0])
     for i in range(args.steps):
         b = (i + args.warmup) % NBATCH
-        loss = step(host[b] if use_graph else to_device(host[b]), b)
+        if use_graph:
+            cur = nxt
+            if i + 1 < args.steps:
+                nxt = stepper.prefetch(*host[(i + 1 + args.warmup) % NBATCH])
+            loss = stepper.step_prefetched(cur, n_real[b])
+        else:
+            loss = step(to_device(host[b]), b)
         _ = float(loss.item())                      # device -> host read of the step's result
         pairs_e2e += batches[b]["pairs"]
         h2d += h2d_bytes(host[b])

@@ -214,9 +214,50 @@ class CapturedTrainStep(object):
             self._tail()
         return s.loss
 
-    @property
-    def last_logits(self):
-        return None
+    # ---------------------------------------------------------------------------------------------------------
+    def prefetch(self, query, document, labels, kw):
+        """Start copying the NEXT batch (host, pinned) to device staging buffers on a side stream while the current step
+        runs; returns a handle to pass to step_prefetched(). The staging -> static copy is device to device (microseconds)."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {}
+        key = (tuple(query.shape), tuple(document.shape), tuple(kw[K.DocContentNoPaddingEvidence].shape),
+               str(kw[K.Evd_Docs_Adj].dtype))
+        # two staging sets per shape, used alternately: the set filled now is not the one the running step reads from
+        sets = self._staging.setdefault(key, [None, None, 0])
+        slot = sets[2] & 1
+        sets[2] += 1
+        dev = self.device
+        new = lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev)
+        if sets[slot] is None:
+            st = {"query": new(query), "document": new(document), "labels": new(labels),
+                  "e_lens": new(kw[K.DocLensIndices][2]), "event": torch.cuda.Event()}
+            for k in _TENSOR_KEYS:
+                if k in kw and torch.is_tensor(kw[k]):
+                    st[k] = new(kw[k])
+            sets[slot] = st
+        st = sets[slot]
+        self._copy_stream.wait_stream(torch.cuda.current_stream())     # the staging set may still be read by an older step
+        with torch.cuda.stream(self._copy_stream):
+            st["query"].copy_(query, non_blocking=True)
+            st["document"].copy_(document, non_blocking=True)
+            st["labels"].copy_(labels, non_blocking=True)
+            st["e_lens"].copy_(kw[K.DocLensIndices][2], non_blocking=True)
+            for k in _TENSOR_KEYS:
+                if k in kw and torch.is_tensor(kw[k]):
+                    st[k].copy_(kw[k], non_blocking=True)
+            st["event"].record(self._copy_stream)
+        kw_dev = dict(kw)
+        for k in _TENSOR_KEYS:
+            if k in st:
+                kw_dev[k] = st[k]
+        kw_dev[K.DocLensIndices] = (None, None, st["e_lens"])
+        return (st, kw_dev)
+
+    def step_prefetched(self, handle, n_real_claims: Optional[int] = None) -> torch.Tensor:
+        st, kw_dev = handle
+        torch.cuda.current_stream().wait_event(st["event"])
+        return self.step(st["query"], st["document"], st["labels"], kw_dev, n_real_claims)
 
     def n_graphs(self) -> int:
         return len(self.slots)

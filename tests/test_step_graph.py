@@ -129,3 +129,25 @@ def test_captured_step_with_optimizer_trains_like_eager():
     assert np.allclose(le, lc, rtol=0, atol=1e-6), ("captured step drifted from the eager step", le, lc)
     for a, b in zip(pe, pc):
         assert float((a - b).abs().max()) < 1e-6
+
+
+@pytest.mark.gpu
+def test_prefetched_inputs_give_the_same_step():
+    from get_b200.model import Graph_basedSemantiStructure
+    from get_b200.step_graph import CapturedTrainStep
+    dev = "cuda"
+    w = synthetic.get_workload("snopes", batch_claims=4, vocab=300, n_article_sources=8)
+    batches = [pad_batch(synthetic.make_batch(w, seed=s), 32) for s in (5, 6, 7)]
+    host = [synthetic.batch_to_torch(b, device="cpu", pin=True) for b in batches]
+    torch.manual_seed(2)
+    m = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=True)).to(dev).eval()
+    stepper = CapturedTrainStep(m)
+    direct = [float(stepper.step(*host[i], batches[i]["n_real_claims"])) for i in range(3)]
+    nxt = stepper.prefetch(*host[0])
+    got = []
+    for i in range(3):
+        cur = nxt
+        if i + 1 < 3:
+            nxt = stepper.prefetch(*host[i + 1])
+        got.append(float(stepper.step_prefetched(cur, batches[i]["n_real_claims"])))
+    assert direct == got
