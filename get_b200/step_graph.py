@@ -68,8 +68,47 @@ def pad_batch(batch: Dict, multiple: int) -> Dict:
                                                          rep0(batch[K.DocContentNoPaddingEvidence], extra)])
     out[K.Evd_Docs_Adj] = np.concatenate([batch[K.Evd_Docs_Adj], rep0(batch[K.Evd_Docs_Adj], extra)])
     out["e_lens"] = np.concatenate([batch["e_lens"], rep0(batch["e_lens"], extra)])
+    if "raw_doc_tokens" in batch:
+        out["raw_query_tokens"] = np.concatenate([batch["raw_query_tokens"], rep0(batch["raw_query_tokens"], nd)])
+        out["raw_query_lens"] = np.concatenate([batch["raw_query_lens"], rep0(batch["raw_query_lens"], nd)])
+        out["raw_doc_tokens"] = np.concatenate([batch["raw_doc_tokens"], rep0(batch["raw_doc_tokens"], extra)])
+        out["raw_doc_lens"] = np.concatenate([batch["raw_doc_lens"], rep0(batch["raw_doc_lens"], extra)])
     out["pairs"] = B1 + extra
     return out
+
+
+def token_batch_to_host(batch: Dict, pin: bool = True):
+    """The compact host-side form of a mini-batch: raw token ids + counts + sources + labels, a few
+    hundred kB instead of the 18.8 MB of dense float64 adjacencies. Returns a dict of (pinned) CPU tensors."""
+    def t(x):
+        y = torch.from_numpy(np.ascontiguousarray(x))
+        return y.pin_memory() if pin and torch.cuda.is_available() else y
+    return {"q_tok": t(batch["raw_query_tokens"]), "q_len": t(batch["raw_query_lens"]), "d_tok": t(batch["raw_doc_tokens"]),
+            "d_len": t(batch["raw_doc_lens"]), "cnt": t(batch[K.EvidenceCountPerQuery]), "labels": t(batch["labels"]),
+            "q_src": t(batch[K.QuerySources]), "d_src": t(batch[K.DocSources]),
+            "n": int(batch[K.FIXED_NUM_EVIDENCES]), "window": int(batch["window"]),
+            "L": int(batch["query"].shape[1]), "R": int(batch[K.DocContentNoPaddingEvidence].shape[1])}
+
+
+def device_batch_from_tokens(tb: Dict, device):
+    """Compact host batch -> (query, document, labels, kwargs) on the device in the fitter's calling convention, with the
+    word graphs built by get_build_word_graphs (no host syncs: every shape comes from the host-side tensors)."""
+    from .graph_build import build_word_graphs
+    mv = lambda x: x.to(device, non_blocking=True)
+    q_nodes, q_adj, q_n = build_word_graphs(mv(tb["q_tok"]), mv(tb["q_len"]), tb["L"], tb["window"])
+    d_nodes, d_adj, d_n = build_word_graphs(mv(tb["d_tok"]), mv(tb["d_len"]), tb["R"], tb["window"])
+    cnt = mv(tb["cnt"])
+    B, n, R, b1 = tb["q_tok"].shape[0], tb["n"], tb["R"], tb["d_tok"].shape[0]
+    seg = torch.repeat_interleave(torch.arange(B, device=device), cnt, output_size=b1)
+    off = torch.cumsum(cnt, 0) - cnt
+    slot = seg * n + (torch.arange(b1, device=device) - off[seg])
+    document = torch.zeros((B * n, R), dtype=torch.int64, device=device)
+    document.index_copy_(0, slot, d_nodes)
+    kw = {K.Query_lens: q_n.to(torch.int64), K.Doc_lens: None, K.DocLensIndices: (None, None, d_n.to(torch.int64)),
+          K.QueryLensIndices: (None, None, q_n.to(torch.int64)), K.QuerySources: mv(tb["q_src"]), K.DocSources: mv(tb["d_src"]),
+          K.DocContentNoPaddingEvidence: d_nodes, K.EvidenceCountPerQuery: cnt, K.FIXED_NUM_EVIDENCES: n,
+          K.Query_Adj: q_adj, K.Evd_Docs_Adj: d_adj}
+    return q_nodes, document.view(B, n, R), mv(tb["labels"]), kw
 
 
 class _Slot(object):
@@ -237,7 +276,8 @@ class CapturedTrainStep(object):
                     st[k] = new(kw[k])
             sets[slot] = st
         st = sets[slot]
-        self._copy_stream.wait_stream(torch.cuda.current_stream())     # the staging set may still be read by an older step
+        if st.get("consumed") is not None:         # the step that last read this staging set has copied it out
+            self._copy_stream.wait_event(st["consumed"])
         with torch.cuda.stream(self._copy_stream):
             st["query"].copy_(query, non_blocking=True)
             st["document"].copy_(document, non_blocking=True)
@@ -255,9 +295,14 @@ class CapturedTrainStep(object):
         return (st, kw_dev)
 
     def step_prefetched(self, handle, n_real_claims: Optional[int] = None) -> torch.Tensor:
+        """Call order for full overlap: loss = step_prefetched(h_i); h_next = prefetch(batch_{i+1}); read loss."""
         st, kw_dev = handle
         torch.cuda.current_stream().wait_event(st["event"])
-        return self.step(st["query"], st["document"], st["labels"], kw_dev, n_real_claims)
+        loss = self.step(st["query"], st["document"], st["labels"], kw_dev, n_real_claims)
+        if st.get("consumed") is None:
+            st["consumed"] = torch.cuda.Event()
+        st["consumed"].record()       # (recorded after the replay: a little late, but it never delays the next-but-one copy)
+        return loss
 
     def n_graphs(self) -> int:
         return len(self.slots)

@@ -141,12 +141,18 @@ def make_batch(w: Workload, seed: int = 123756, n_claims: Optional[int] = None, 
     flat_doc = np.zeros((B1, R), np.int64)
     flat_adj = np.zeros((B1, R, R), adj_dtype)
     e_lens = np.zeros((B1,), np.int64)
+    # the raw (not de-duplicated) token sequences the graphs are built from: input of the device-side graph construction
+    raw_q = np.zeros((B, L), np.int64)
+    raw_q_len = np.zeros((B,), np.int32)
+    raw_d = np.zeros((B1, R), np.int64)
+    raw_d_len = np.zeros((B1,), np.int32)
     g = 0
     for c in range(B):
         qlen = int(np.clip(rng.poisson(9.6), 3, L))
         toks = rng.integers(2, w.vocab, size=qlen)
         nodes, adj, nn = word_graph(toks, L, w.window)
         query[c], query_adj[c], query_lens[c] = nodes, adj, nn
+        raw_q[c, :qlen], raw_q_len[c] = toks, qlen
         for j in range(int(cnt[c])):
             pool = rng.integers(2, w.vocab, size=min(w.evd_pool, w.vocab - 2))
             dlen = R if rng.random() < 0.9 else int(rng.integers(max(2, R // 4), R + 1))
@@ -155,11 +161,14 @@ def make_batch(w: Workload, seed: int = 123756, n_claims: Optional[int] = None, 
             document[c, j], docs_lens[c, j] = nodes, nn
             doc_sources[c, j] = rng.integers(0, w.n_article_sources)
             flat_doc[g], flat_adj[g], e_lens[g] = nodes, adj, nn
+            raw_d[g, :dlen], raw_d_len[g] = toks, dlen
             g += 1
     labels = (rng.random(B) < w.true_rate).astype(np.int64)
     query_sources = rng.integers(0, w.n_claim_sources, size=(B, 1)).astype(np.int64)
     return {
         "query": query, "document": document, "labels": labels, "e_lens": e_lens, "pairs": B1,
+        "raw_query_tokens": raw_q, "raw_query_lens": raw_q_len, "raw_doc_tokens": raw_d, "raw_doc_lens": raw_d_len,
+        "window": w.window,
         K.Query_lens: query_lens, K.Doc_lens: docs_lens, K.Query_Adj: query_adj,
         K.Evd_Docs_Adj: flat_adj, K.DocContentNoPaddingEvidence: flat_doc,
         K.EvidenceCountPerQuery: cnt, K.FIXED_NUM_EVIDENCES: n,

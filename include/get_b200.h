@@ -243,6 +243,16 @@ int get_dropout_mask_f32(float* out, int64_t numel, float p, uint32_t seed, void
 int get_cross_entropy_f32(const float* logits, const int64_t* labels, int B, int C,
                           float* loss, float* dlogits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Word-graph construction on the device (the host code interactions.py:334-351 `convert_text` + :11-18
+ * `_laplacian_normalize`): tokens (G,T) int64 raw token ids, lengths (G,) int32 valid tokens per text.
+ * nodes (G,N) int64 = distinct tokens of the first min(length, N) positions in first-occurrence order (0 elsewhere),
+ * n_nodes (G,) int32, adj (G,N,N) fp32 = D^-1/2 A D^-1/2 of the sliding-window co-occurrence graph
+ * (|i-j| <= window-1, self loops), evaluated in double like the reference and rounded once to fp32.
+ * ---------------------------------------------------------------------------------------------- */
+int get_build_word_graphs(const int64_t* tokens, const int32_t* lengths, int G, int T, int N, int window,
+                          int64_t* nodes, float* adj, int32_t* n_nodes, void* stream);
+
 /* Library info */
 int get_b200_abi_version(void);
 const char* get_b200_last_error(void);

@@ -357,3 +357,25 @@ def test_segment_ops_masked_mean_cross_entropy_linear():
         assert torch.allclose(got.grad.cpu().double(), ref.grad, atol=1e-4)
     cs = ops.colsum(gy.to(DEV))
     assert torch.allclose(cs.cpu().double(), gy.double().sum(0), atol=1e-5)
+
+
+@pytest.mark.parametrize("T,N,window,vocab", [(100, 100, 3, 140), (100, 100, 5, 60), (100, 100, 9, 3000), (30, 30, 3, 12),
+                                              (57, 100, 3, 40), (120, 100, 3, 150)])
+def test_device_word_graphs_match_host_construction(T, N, window, vocab):
+    """get_build_word_graphs against the restated convert_text + _laplacian_normalize (get_b200.synthetic.word_graph,
+    itself pinned to the reference in tests/test_oracle_golden.py): node lists, counts and fp32 adjacencies identical."""
+    from get_b200 import synthetic
+    from get_b200.graph_build import build_word_graphs
+    rng = np.random.default_rng(T * 31 + window)
+    G = 23
+    toks = rng.integers(2, vocab + 2, size=(G, T)).astype(np.int64)
+    lens = rng.integers(1, T + 1, size=(G,)).astype(np.int32)
+    lens[0], lens[1] = T, 1
+    nodes, adj, nn = build_word_graphs(torch.from_numpy(toks).to(DEV), torch.from_numpy(lens).to(DEV), N, window)
+    for g in range(G):
+        L = int(min(lens[g], N))
+        rn, ra, rc = synthetic.word_graph(toks[g, :L], N, window)
+        assert int(nn[g]) == rc
+        assert np.array_equal(nodes[g].cpu().numpy(), rn)
+        ref32 = torch.from_numpy(ra).float()
+        assert torch.equal(adj[g].cpu(), ref32), "graph %d: max diff %g" % (g, float((adj[g].cpu() - ref32).abs().max()))

@@ -146,8 +146,25 @@ def test_prefetched_inputs_give_the_same_step():
     nxt = stepper.prefetch(*host[0])
     got = []
     for i in range(3):
-        cur = nxt
+        loss = stepper.step_prefetched(nxt, batches[i]["n_real_claims"])
         if i + 1 < 3:
             nxt = stepper.prefetch(*host[i + 1])
-        got.append(float(stepper.step_prefetched(cur, batches[i]["n_real_claims"])))
+        got.append(float(loss))
     assert direct == got
+
+
+@pytest.mark.gpu
+def test_token_batch_builds_the_same_inputs_on_the_device():
+    """Compact (token-id) batch -> device graph construction reproduces the fitter-format tensors exactly."""
+    from get_b200.step_graph import device_batch_from_tokens, token_batch_to_host
+    w = synthetic.get_workload("snopes", batch_claims=6, vocab=300, n_article_sources=8)
+    batch = pad_batch(synthetic.make_batch(w, seed=3), 16)
+    q, d, l, kw = synthetic.batch_to_torch(batch, device="cuda")
+    tq, td, tl, tkw = device_batch_from_tokens(token_batch_to_host(batch), "cuda")
+    assert torch.equal(tq, q) and torch.equal(td, d) and torch.equal(tl, l)
+    assert torch.equal(tkw[K.DocContentNoPaddingEvidence], kw[K.DocContentNoPaddingEvidence])
+    assert torch.equal(tkw[K.Evd_Docs_Adj], kw[K.Evd_Docs_Adj].float())
+    assert torch.equal(tkw[K.Query_Adj], kw[K.Query_Adj].float())
+    assert torch.equal(tkw[K.Query_lens], kw[K.Query_lens])
+    assert torch.equal(tkw[K.DocLensIndices][2], kw[K.DocLensIndices][2])
+    assert torch.equal(tkw[K.EvidenceCountPerQuery], kw[K.EvidenceCountPerQuery])
