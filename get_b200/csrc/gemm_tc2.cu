@@ -56,7 +56,7 @@ struct Tc2Cfg {
   int tstages;           // depth of the TMEM ring of A tiles (64 columns each)
   int a_tmem_col;        // first TMEM column of that ring
   uint32_t a_stage;      // bytes of the A part of one shared-memory stage (raw tile, plus the lo tile in SS mode)
-  int debug;             // perf experiments only (GET_B200_T2_DEBUG): 1 = main MMA only, 2 = splitter skips its work
+  int debug;             // GET_B200_T2_DEBUG=9 with -DGETB_T2_TIMELINE: print the per-role timeline of CTA 0
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -314,12 +314,9 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
             const uint64_t dah = smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t dbh = smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt), dbl = smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
             const uint32_t first = (kb > kb0 || ks > 0) ? 1u : 0u;
-            if (cfg.debug == 3 && !(kb + 1 == kb1 && ks == 0)) continue;   // experiment: (almost) no MMAs
             umma_tf32(d_main, dah, dbh, idesc, first);
-            if (cfg.debug != 1 && cfg.debug != 3) {
-              umma_tf32(d_small, dah, dbl, idesc, first);
-              umma_tf32(d_small, dal, dbh, idesc, 1u);
-            }
+            umma_tf32(d_small, dah, dbl, idesc, first);
+            umma_tf32(d_small, dal, dbh, idesc, 1u);
           }
           }
           umma_commit(&bar_empty[stage]);
@@ -381,7 +378,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           tmem_st_wait();
           tc_fence_before();
           if (++tstage == cfg.tstages) { tstage = 0; tphase ^= 1; }
-        } else if (cfg.debug != 2 && cfg.debug != 3) {
+        } else {
           float4 v[a_chunks];
 #pragma unroll
           for (int i = 0; i < a_chunks; ++i) v[i] = lds128(a_hi + (uint32_t)(t + i * 128) * 16u);
@@ -475,7 +472,6 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
         }
         __syncwarp();
         const int n = n0 + col + rq * 4;
-        if (cfg.debug == 4) continue;    // experiment: no global epilogue traffic
         if ((two || rq < 4) && n < p.N) {
           if (cfg.splits > 1) {
 #pragma unroll
