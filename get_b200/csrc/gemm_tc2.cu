@@ -56,6 +56,8 @@ struct Tc2Cfg {
   int tstages;           // depth of the TMEM ring of A tiles (64 columns each)
   int a_tmem_col;        // first TMEM column of that ring
   uint32_t a_stage;      // bytes of the A part of one shared-memory stage (raw tile, plus the lo tile in SS mode)
+  int single;            // reduced-precision mode (desc->tc_mode == 2): ONE tf32 MMA per k step on the raw operands, no hi/lo
+                         // split, no small-term accumulator (relative error ~1e-3: for the 1e-2 parity class only)
   int debug;             // GET_B200_T2_DEBUG=9 with -DGETB_T2_TIMELINE: print the per-role timeline of CTA 0
 };
 
@@ -231,7 +233,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_bytes = T2_A_TILE;
-      const uint32_t tx = a_bytes + cfg.b_tile * (cfg.split_b ? 1u : 2u);
+      const uint32_t tx = a_bytes + cfg.b_tile * ((cfg.split_b || cfg.single) ? 1u : 2u);
       for (int it = 0; it < n_my; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
         const int nt = item % cfg.ntn, mt = (item / cfg.ntn) % cfg.ntm, z = item / (cfg.ntn * cfg.ntm);
@@ -256,7 +258,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
             for (int a = 0; a < BN / 32; ++a) tma_load_2d(sbh + a * 4096u, &maps.bh[seg], n0 + a * 32, kin, &bar_raw[stage]);
           } else {
             tma_load_2d(sbh, &maps.bh[seg], kin, n0, &bar_raw[stage]);
-            if (!cfg.split_b) tma_load_2d(sbl, &maps.bl[seg], kin, n0, &bar_raw[stage]);
+            if (!cfg.split_b && !cfg.single) tma_load_2d(sbl, &maps.bl[seg], kin, n0, &bar_raw[stage]);
           }
           if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
         }
@@ -287,7 +289,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
         const uint32_t d_small = d_main + (uint32_t)BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bar_raw[stage], phase);
-          mbar_wait(&bar_ready[stage], phase);
+          if (!cfg.single) mbar_wait(&bar_ready[stage], phase);
           tc_fence_after();
           if (kb == kb0) T2_DBG(1, it * 3 + 1);
           if (it == 0 && kb - kb0 >= 4 && kb - kb0 < 7) T2_DBG(1, 12 + (kb - kb0 - 4) * 2);
@@ -295,7 +297,12 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
           const uint32_t a_lo = a_hi + T2_A_TILE;
           const uint32_t b_hi = a_hi + cfg.a_stage;
           const uint32_t b_lo = b_hi + cfg.b_tile;
-          if (cfg.a_tmem) {
+          if (cfg.single) {
+#pragma unroll
+            for (int ks = 0; ks < T2_BK / 8; ++ks)
+              umma_tf32(d_main, smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt),
+                        idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+          } else if (cfg.a_tmem) {
             const uint32_t ta_hi = tmem_base + (uint32_t)(cfg.a_tmem_col + tstage * 64);
             const uint32_t ta_lo = ta_hi + 32u;
 #pragma unroll
@@ -339,6 +346,8 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
     const int t = tid - 64;   // 0..127
     int stage = 0, tstage = 0;
     uint32_t phase = 0, tphase = 0;
+    if (cfg.single) goto t2_role_done;                                // raw operands go straight to the tensor core
+    {
     constexpr int a_chunks = T2_A_TILE / 16 / 128;                   // 16-byte chunks per thread in the A tile
     const int b_chunks = cfg.split_b ? (int)(cfg.b_tile / 16) : 0;   // total chunks of the B tile
     for (int it = 0; it < n_my; ++it) {
@@ -410,6 +419,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
         if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
       }
     }
+    }
   } else {
     // =========================================== epilogue ===============================================
     // TMEM hands every thread one output ROW; a per-warp 32 x 32 staging tile in shared memory turns that into 8 lanes
@@ -440,12 +450,16 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
         const bool two = col + 16 < BN;
         uint32_t rm[16], rs[16], rm2[16], rs2[16];
         tmem_ld16_nowait(t_main + (uint32_t)col, rm);
-        tmem_ld16_nowait(t_small + (uint32_t)col, rs);
+        if (!cfg.single) tmem_ld16_nowait(t_small + (uint32_t)col, rs);
         if (two) {
           tmem_ld16_nowait(t_main + (uint32_t)col + 16u, rm2);
-          tmem_ld16_nowait(t_small + (uint32_t)col + 16u, rs2);
+          if (!cfg.single) tmem_ld16_nowait(t_small + (uint32_t)col + 16u, rs2);
         }
         tmem_ld_wait();
+        if (cfg.single) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { rs[e] = 0u; rs2[e] = 0u; }
+        }
         if (col == last_col) {           // last chunk of this accumulator set for this warp: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&bar_acce[acc]);
@@ -517,6 +531,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ Tc
       }
     }
   }
+t2_role_done:
   tc_fence_before();
   __syncthreads();
 #ifdef GETB_T2_TIMELINE
@@ -615,6 +630,7 @@ static int t2_pad(int n, int q) { return (n + q - 1) / q * q; }
 static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
   if (d->tc_mode < 1) return 1;
   if (p.M < 1 || p.N < 8) return 1;
+  const int single = d->tc_mode == 2 ? 1 : 0;
   if (p.drop_thr) return 1;                                   // A-operand dropout: register-staged kernel (gemm_tc.cu)
   if (!p.vec_epi || (p.N & 3)) return 1;                      // the epilogue works on aligned float4 quads only
   memset(&cfg, 0, sizeof(cfg));
@@ -622,6 +638,7 @@ static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
   cfg.a_mn = p.A[0].trans;
   cfg.b_mn = presplit ? 0 : p.B[0].trans;
   cfg.split_b = presplit ? 0 : 1;
+  cfg.single = single;
   for (int s = 0; s < p.nseg; ++s) {
     if (p.A[s].rowidx) return 1;                              // gathered A: register-staged kernel
     if (p.A[s].trans != cfg.a_mn || !aligned16(p.A[s].ptr) || (p.A[s].ld % 4) != 0) return 1;
@@ -697,8 +714,8 @@ static int tc2_plan(const get_gemm_desc* d, const GemmParams& p, Tc2Cfg& cfg) {
     cfg.tmem_cols = tc;
   }
   cfg.b_tile = (uint32_t)cfg.BN * 128u;
-  cfg.a_stage = cfg.a_tmem ? (uint32_t)T2_A_TILE : 2u * T2_A_TILE;
-  cfg.stage_bytes = cfg.a_stage + 2u * cfg.b_tile;
+  cfg.a_stage = (cfg.a_tmem || cfg.single) ? (uint32_t)T2_A_TILE : 2u * T2_A_TILE;
+  cfg.stage_bytes = cfg.a_stage + (cfg.single ? 1u : 2u) * cfg.b_tile;
   int stages = (224 * 1024 - 2048 - T2_STG_BYTES) / (int)cfg.stage_bytes;
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
   if (stages < 2) return 1;

@@ -62,7 +62,7 @@ class GGNN(nn.Module):
                 self.linearh0.linear.weight, self.linearh0.linear.bias,
                 self.linearh1.linear.weight, self.linearh1.linear.bias)
 
-    def forward(self, adj, x=None, *, table=None, ids=None, keep=None, pre_agg=None, seed=None):
+    def forward(self, adj, x=None, *, table=None, ids=None, keep=None, pre_agg=None, seed=None, exact_fwd=False):
         """Reference call: forward(adj, x). Extensions used inside this package: (table, ids) = frozen embedding
         table + token ids instead of x (gather fused into the projection), keep / pre_agg from the GSL kernel,
         explicit dropout seed (tests)."""
@@ -70,7 +70,7 @@ class GGNN(nn.Module):
         if p > 0 and seed is None:
             seed = ops.new_seed()
         adj = adj.float()
-        return ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params())
+        return ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params(), exact_fwd=exact_fwd)
 
 
 class GSL(nn.Module):
@@ -117,7 +117,7 @@ class GGNN_with_GSL(nn.Module):
         p = self.feat_prop2.p_drop if self.training else 0.0
         if seeds is None:
             seeds = tuple(ops.new_seed() for _ in range(3)) if self.training else (0, 0, 0)
-        f1 = self.feat_prop1(adj, feat, table=table, ids=ids, seed=seeds[0])
+        f1 = self.feat_prop1(adj, feat, table=table, ids=ids, seed=seeds[0], exact_fwd=True)   # decides the kept node set
         wp, gate = self._scorer_params()
         ps = self.word_scorer1.p_drop if self.training else 0.0
         assert ps == p or ps == 0 or p == 0, "scorer / layer-2 dropout rates are the same value in the reference"

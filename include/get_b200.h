@@ -100,7 +100,10 @@ typedef struct get_gemm_desc {
    *      K % 4 == 0, K >= 32), no split-K, B pre-split.
    * Pre-split B: two k-contiguous (N, K[s]) row-major matrices B_hi[s] (tf32-rounded) and B_lo[s] (= B - B_hi) with
    * leading dimension ld_split[s] (see get_split_tf32_f32; a transposed B is simply split into a k-contiguous copy).
-   * B[s] stays the original operand for the fallback. tc_n_tiles: CTA tiles along N (0 = auto). */
+   * B[s] stays the original operand for the fallback. tc_n_tiles: CTA tiles along N (0 = auto).
+   * tc_mode == 2: reduced-precision mode of kernel (a): ONE tf32 pass on the raw operands (no hi/lo split, B_lo unused),
+   * relative error ~1e-3 -- for the 1e-2 parity class (BASELINE.json configs[2]) and never for the layer that feeds the
+   * GSL top-k. */
   const float* B_hi[GET_GEMM_MAX_SEG];
   const float* B_lo[GET_GEMM_MAX_SEG];
   int64_t ld_split[GET_GEMM_MAX_SEG];
