@@ -311,30 +311,55 @@ def run_ours(args):
     t_dev = e0.elapsed_time(e1) / 1e3
 
     # ---- timed region 2: end to end from pinned host memory --------------------------------------
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e2.record()
-    pairs_e2e, h2d, d2h = 0, 0, 0
-    nxt = None
-    if use_graph:                                   # the next batch's H2D copy overlaps the current step (side stream)
-        b0 = args.warmup % NBATCH
-        nxt = stepper.prefetch(*host[b0])
-    for i in range(args.steps):
-        b = (i + args.warmup) % NBATCH
-        if use_graph:
-            loss = stepper.step_prefetched(nxt, n_real[b])             # device-to-device copy-in + one graph replay
-            if i + 1 < args.steps:                                     # H2D of the next batch while this step runs
-                nxt = stepper.prefetch(*host[(i + 1 + args.warmup) % NBATCH])
-        else:
-            loss = step(to_device(host[b]), b)
-        _ = float(loss.item())                      # device -> host read of the step's result
-        pairs_e2e += batches[b]["pairs"]
-        h2d += h2d_bytes(host[b])
-        d2h += 4
-    e3.record()
-    barrier()
-    t_e2e = max(time.perf_counter() - t0, e2.elapsed_time(e3) / 1e3)
+    def e2e_pass(nsteps):
+        """nsteps end-to-end steps: per step the H2D copy of that step's inputs (overlapped with the previous step's
+        compute on a side stream when graphs are on), the step, and a D2H read of the loss."""
+        npairs, nh2d = 0, 0
+        nxt = stepper.prefetch(*host[args.warmup % NBATCH]) if use_graph else None
+        for i in range(nsteps):
+            b = (i + args.warmup) % NBATCH
+            if use_graph:
+                loss = stepper.step_prefetched(nxt, n_real[b])             # device-to-device copy-in + one graph replay
+                if i + 1 < nsteps:                                         # H2D of the next batch while this step runs
+                    nxt = stepper.prefetch(*host[(i + 1 + args.warmup) % NBATCH])
+            else:
+                loss = step(to_device(host[b]), b)
+            _ = float(loss.item())                      # device -> host read of the step's result
+            npairs += batches[b]["pairs"]
+            nh2d += h2d_bytes(host[b])
+        return npairs, nh2d
+
+    e2e_pass(NBATCH)                                    # untimed: staging buffers of every batch shape get allocated here
+    # three timed passes of K steps each; the MEDIAN pass is reported and all three are listed: on the shared hosts of this
+    # pool single passes of this loop (a host sync every step) were observed to vary by tens of percent run to run
+    e2e_times = []
+    for _ in range(3):
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e2.record()
+        pairs_e2e, h2d = e2e_pass(args.steps)
+        e3.record()
+        barrier()
+        e2e_times.append(max(time.perf_counter() - t0, e2.elapsed_time(e3) / 1e3))
+    d2h = 4 * args.steps
+    t_e2e = sorted(e2e_times)[1]
+
+    # ---- diagnostic: what the pinned host -> device path delivers on this (shared) host right now ---------------
+    h2d_diag = None
+    if rank == 0:
+        big = max((t for t in host[0][3].values() if torch.is_tensor(t)), key=lambda t: t.numel() * t.element_size())
+        dst = torch.empty(big.shape, dtype=big.dtype, device=dev)
+        rates = []
+        for _ in range(8):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dst.copy_(big, non_blocking=True)
+            b_.record()
+            torch.cuda.synchronize()
+            rates.append(big.numel() * big.element_size() / (a.elapsed_time(b_) * 1e-3) / 1e9)
+        h2d_diag = {"bytes": big.numel() * big.element_size(), "pinned": bool(big.is_pinned()),
+                    "GBs_min": min(rates), "GBs_median": float(np.median(rates)), "GBs_max": max(rates)}
 
     # ---- timed region 3: end to end from the COMPACT host format (SURVEY 8f: token ids instead of dense float64
     #      adjacencies; the word graphs are built on the device by get_build_word_graphs) -----------------------------
@@ -343,8 +368,9 @@ def run_ours(args):
         from get_b200.step_graph import device_batch_from_tokens, token_batch_to_host
         tbs = [token_batch_to_host(b) for b in padded]
         tok_bytes = [sum(v.numel() * v.element_size() for v in tb.values() if torch.is_tensor(v)) for tb in tbs]
-        for b in range(NBATCH):                   # graphs for the fp32-adjacency input signature
-            stepper.step(*device_batch_from_tokens(tbs[b], dev), n_real[b])
+        for rep in range(2):                      # graphs for the fp32-adjacency input signature, then an allocator warm-up pass
+            for b in range(NBATCH):
+                float(stepper.step(*device_batch_from_tokens(tbs[b], dev), n_real[b]).item())
         barrier()
         e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -429,7 +455,8 @@ def run_ours(args):
                                       "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps}),
             "clocks": clocks,
             "e2e": {"value": pairs_e2e / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "passes_ms_per_step": [1e3 * t / args.steps for t in e2e_times], "reported": "median of 3 passes of K steps"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "graph_smem_kernel<FUSED=1> (get_gsl_fused_f32), train-mode dropout, the bench batches' own launches replayed back to back",
                          "bound": "hbm", "achieved": achieved,
@@ -438,6 +465,7 @@ def run_ours(args):
                          "avg_launch_ms": gsl_avg_ms, "algorithmic_bytes_per_launch": gsl_bytes,
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
             "e2e_token_inputs": e2e_tok,
+            "h2d_diagnostic": h2d_diag,
             "roofline_stream": stream_roof,
             "cuda_graphs": {"enabled": use_graph, "graphs": stepper.n_graphs() if use_graph else 0, "pad_pairs_to": PAD_PAIRS if use_graph else 0},
             "cpu_baseline": {"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",

@@ -12,9 +12,14 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+import os
+
 from . import ops
 from .keywords import KeyWordSettings
 from .modules import GGNN, GGNN_with_GSL, LSTM, ConcatNotEqualSelfAtt, Linear
+
+
+_OVERLAP_CLAIM = os.environ.get("GET_B200_OVERLAP_CLAIM", "1") != "0"
 
 
 def _init_weights(m):
@@ -90,6 +95,7 @@ class Graph_basedSemantiStructure(nn.Module):
         self.out[0].apply(_init_weights)
         self.out[1].apply(_init_weights)
         self.dropout_seeds = None   # tests: dict(claim=, feat_prop1=, word_scorer1=, feat_prop2=) fixed seeds
+        self._side_stream = None
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
@@ -123,14 +129,24 @@ class Graph_basedSemantiStructure(nn.Module):
         seg, slot, offsets = self._segments(evd_cnt, b1, n)
         emb_fused = not self.embedding.weight.requires_grad
 
-        # claim graph -> masked mean (gbss.py:144-155)
+        # claim graph -> masked mean (gbss.py:144-155). The claim branch is a chain of small kernels (B*30 rows, a few
+        # dozen CTAs each) that is independent of the evidence branch until the word-level attention: it runs on a side
+        # stream and fills the tails of the evidence branch's kernels (forward and, through autograd's stream
+        # bookkeeping, backward). Only when every cached weight split is current -- they are refreshed lazily by the
+        # first GEMM that needs them, which must not race across streams.
         q_adj = kargs[K.Query_Adj]
-        if emb_fused:
-            q_hid = self.ggnn4claim_1(q_adj, table=self.embedding.weight, ids=query, seed=seeds.get("claim"))
-        else:
-            q_hid = self.ggnn4claim_1(q_adj, self.embedding(query.long()), seed=seeds.get("claim"))
-        q_claim = ops.MaskedMeanFn.apply(q_hid, query, kargs[K.Query_lens])           # (B, H)
-        query_repr = ops.SegmentExpandFn.apply(q_claim, seg, offsets)                # (B1, H)
+        cur = torch.cuda.current_stream()
+        fork = _OVERLAP_CLAIM and ops.refresh_weight_splits()
+        if fork:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=query.device)
+            self._side_stream.wait_stream(cur)
+        with torch.cuda.stream(self._side_stream if fork else cur):
+            if emb_fused:
+                q_hid = self.ggnn4claim_1(q_adj, table=self.embedding.weight, ids=query, seed=seeds.get("claim"))
+            else:
+                q_hid = self.ggnn4claim_1(q_adj, self.embedding(query.long()), seed=seeds.get("claim"))
+            q_claim = ops.MaskedMeanFn.apply(q_hid, query, kargs[K.Query_lens])       # (B, H)
 
         # evidence graphs (gbss.py:107)
         blk_seeds = None
@@ -140,6 +156,11 @@ class Graph_basedSemantiStructure(nn.Module):
             doc_out = self.ggnn_with_gsl(doc_adj, table=self.embedding.weight, ids=doc, seeds=blk_seeds)
         else:
             doc_out = self.ggnn_with_gsl(doc_adj, self.embedding(doc.long()), seeds=blk_seeds)
+
+        if fork:
+            cur.wait_stream(self._side_stream)
+            q_claim.record_stream(cur)
+        query_repr = ops.SegmentExpandFn.apply(q_claim, seg, offsets)                # (B1, H)
 
         # word-level attention (gbss.py:110, 173-193)
         avg, word_att = self.self_att_word(query_repr, doc_out, doc >= 1)

@@ -146,6 +146,28 @@ def prepare_split_table():
     _split_table = (raw.to(ent[1].device), len(keys), blocks, keys)
 
 
+def refresh_weight_splits() -> bool:
+    """Bring every cached weight split up to date NOW, on the current stream (one launch). Returns True when the cache is
+    populated and current afterwards -- the condition under which independent branches of the model may run on side
+    streams without racing on the lazily refreshed splits."""
+    global _split_table
+    if not _split_cache:
+        return False
+    stale = any(e[0][1] != _split_epoch for e in _split_cache.values())
+    if stale:
+        if _split_table is None:
+            if torch.cuda.is_current_stream_capturing():
+                return False
+            prepare_split_table()
+        tab, n, blocks, keys = _split_table
+        _lib.check(_lib.load().get_split_tf32_multi_f32(tab.data_ptr(), n, blocks, _stream()), "get_split_tf32_multi_f32")
+        for k2 in keys:
+            e2 = _split_cache.get(k2)
+            if e2 is not None:
+                e2[0] = (e2[0][0], _split_epoch)
+    return all(e[0][1] == _split_epoch for e in _split_cache.values())
+
+
 def split_weight(b: torch.Tensor):
     """(hi, lo) k-contiguous TF32 split of a weight view b (logical (N, K), any strides), cached per
     (storage address, shape, strides). Refreshed when the weights change: the optimizer post-step hook / a captured step
