@@ -222,6 +222,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") and logs go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     w = synthetic.get_workload(WORKLOAD)
     ops.set_precision(args.precision)
@@ -440,7 +442,7 @@ def run_ours(args):
             with open(tpath) as fh:
                 traffic = json.load(fh).get("dram_bytes_per_launch")
         cpu = None
-        if world == 1 or True:
+        if world == 1:                 # the CPU baseline is an N=1 measurement (other ranks' host threads would disturb it)
             cores = os.cpu_count() or 1
             cpu = cpu_baseline(w, steps=5, warmup=1, cores=cores, max_seconds=25.0)
         line = {
@@ -468,8 +470,8 @@ def run_ours(args):
             "h2d_diagnostic": h2d_diag,
             "roofline_stream": stream_roof,
             "cuda_graphs": {"enabled": use_graph, "graphs": stepper.n_graphs() if use_graph else 0, "pad_pairs_to": PAD_PAIRS if use_graph else 0},
-            "cpu_baseline": {"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]},
+            "cpu_baseline": ({"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                              "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]} if cpu is not None else None),
         }
         print(json.dumps(line))
         sys.stdout.flush()
