@@ -94,3 +94,41 @@ def test_trainable_parameters_exclude_inert_ones():
     gold = load_golden("tiny_snopes")
     with_grad = sorted(k[5:] for k in gold if k.startswith("grad/"))
     assert sorted(names) == with_grad     # exactly the parameters that get a gradient in the reference
+
+
+def _worker_local_gather(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from get_b200.ddp import FlatGradAllReduce
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))]
+    red = FlatGradAllReduce(params)
+    red.init_collective()                      # symmetric, outside any step
+    for p in params:
+        p.grad = torch.full_like(p, float(rank + 1))
+    red.reduce(collective=False)               # warm-up semantics: gather only, no communication
+    local = red.flat.clone()
+    for p in params:
+        p.grad = torch.full_like(p, float(rank + 1))
+    red.reduce()                               # the real step: averaged over ranks
+    q.put((rank, local.tolist(), red.flat.tolist(), all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, red.views))))
+    dist.destroy_process_group()
+
+
+def test_reduce_without_collective_only_gathers_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_local_gather, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for rank, local, reduced, aliased in res:
+        assert local == [float(rank + 1)] * 11
+        assert reduced == [1.5] * 11
+        assert aliased
