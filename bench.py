@@ -40,6 +40,55 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class NvmlClockSampler(object):
+    """SM clock and throttle reasons read through NVML every ~2 ms DURING the timed region (the timed region of the default
+    run lasts ~0.1 s, too short for nvidia-smi's polling). Falls back to the nvidia-smi sampler below when NVML is missing."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        try:                      # NVML ignores CUDA_VISIBLE_DEVICES: address the device by UUID when torch exposes it
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) and bytes is not str else uuid)
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self.sm, self.mask, self.stop_flag, self.thread = [], 0, False, None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "samples": len(self.sm),
+                "reasons": reasons, "source": "nvml"}
+
+
+def make_clock_sampler(index: int):
+    try:
+        return NvmlClockSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -291,7 +340,7 @@ def run_ours(args):
     barrier()
 
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------
-    sampler = ClockSampler(local_rank)
+    sampler = make_clock_sampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count() + (stepper.replayed_launches if use_graph else 0)
