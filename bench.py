@@ -136,6 +136,26 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout must carry exactly ONE JSON line: point fd 1 at stderr for the whole run (library banners such as NCCL's
+    version line, warnings, device printf) and restore it only to emit the result."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line))
+    sys.stdout.flush()
+
+
 def make_batches(w, n, base_seed):
     from get_b200 import synthetic
     return [synthetic.make_batch(w, seed=base_seed + 1000 * i) for i in range(n)]
@@ -169,7 +189,7 @@ def run_reference(args):
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline(w, steps, warmup, cores, max_seconds=40.0):
@@ -522,8 +542,7 @@ def run_ours(args):
             "cpu_baseline": ({"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                               "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]} if cpu is not None else None),
         }
-        print(json.dumps(line))
-        sys.stdout.flush()
+        emit(line)
     if world > 1:
         # Tearing down a communicator whose collectives live inside captured CUDA graphs can block in ncclCommDestroy;
         # every rank is done once it passes this barrier, so leave without destroying the process group.
@@ -544,6 +563,7 @@ def main():
                     help="fp32 = 3xTF32 everywhere (the judged configuration); fast = single tf32 pass outside the GSL top-k chain")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
+    guard_stdout()
     if args.impl == "reference":
         if args.steps > 12:
             args.steps = 12          # bounded sample: ~1 s of CPU work per step
