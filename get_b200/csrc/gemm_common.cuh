@@ -1,4 +1,4 @@
-// Shared between the SIMT (exact fp32) and tcgen05 (3xTF32) GEMM kernels: launch parameters and the fused epilogues.
+// Exact-fp32 SIMT GEMM (small / odd contractions): launch parameters and the fused epilogues.
 #pragma once
 #include "common.cuh"
 
@@ -183,12 +183,4 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, int m, int n, flo
 
 // host side: validate a descriptor and fill the kernel parameters (gemm_simt.cu)
 int gemm_build_params(const get_gemm_desc* d, GemmParams& p);
-// tcgen05 path (gemm_tc.cu): returns 0 when launched, 1 when the descriptor is not eligible (caller falls back to SIMT)
-int gemm_tc_launch(const get_gemm_desc* d, const GemmParams& p, cudaStream_t st);
-// persistent TMA-fed tcgen05 path (gemm_tc2.cu): 0 launched, 2 launched with split-K partials in the workspace (p.split_k
-// updated; the caller runs the reduction), 1 not eligible, <0 error
-int gemm_tc2_launch(const get_gemm_desc* d, GemmParams& p, cudaStream_t st);
-int gemm_tc2_plan_splits(const get_gemm_desc* d, const GemmParams& p);   // -1 not eligible, else number of k splits
-int gemm_tc_eligible(const get_gemm_desc* d, const GemmParams& p);       // gemm_tc.cu: 1 eligible
-
 }  // namespace getb

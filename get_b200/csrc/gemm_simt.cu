@@ -289,11 +289,6 @@ extern "C" int get_gemm_f32_launches(const get_gemm_desc* d) {
   GemmParams p;
   if (gemm_build_params(d, p) != 0) return -1;
   if (p.M == 0 || p.N == 0) return 0;
-  if (d->tc_mode >= 1) {
-    const int sp = gemm_tc2_plan_splits(d, p);
-    if (sp > 0) return sp > 1 ? 2 : 1;
-    if (gemm_tc_eligible(d, p)) return 1;
-  }
   return p.split_k > 1 ? 2 : 1;
 }
 
@@ -303,20 +298,6 @@ extern "C" int get_gemm_f32(const get_gemm_desc* d, void* stream) {
   if (rc != 0) return rc;
   if (p.M == 0 || p.N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->tc_mode >= 1) {
-    const int rc2 = gemm_tc2_launch(d, p, st);
-    if (rc2 < 0) return rc2;
-    if (rc2 == 0) return 0;
-    if (rc2 == 2) {            // split-K partial tiles are in the workspace: fixed-order reduction + epilogue
-      const int64_t nq = (int64_t)p.M * ((p.N + 3) / 4);
-      gemm_splitk_reduce_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(p);
-      GETB_CHECK_LAUNCH("gemm_splitk_reduce_kernel");
-      return 0;
-    }
-    const int trc = gemm_tc_launch(d, p, st);
-    if (trc == 0) return 0;
-    if (trc < 0) return trc;   // launch error; trc == 1: not eligible -> exact SIMT path below
-  }
   const int64_t ntm = (p.M + BM - 1) / BM;
   const int64_t nblk = ntm * p.ntn;
   GETB_REQUIRE(nblk < (int64_t)2147483647, "get_gemm_f32: too many tiles");

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace getb {
 
@@ -43,6 +44,10 @@ struct GraphParams {
   const uint32_t* salt; // device word added to both seeds inside the kernels
   float* score;        // (G,N) or null
   uint8_t* keep_out;   // (G,N)
+  // optional bf16-plane copy of the output rows (operand of the next tensor-core contraction); `out` may then be null
+  __nv_bfloat16* out_p;
+  int64_t ld_p, ps_p;
+  int np_p, pad_one;
 };
 
 // smem layout: [adj N*NP floats (if adj_in_smem)] [sp N] [score N] [keep N bytes (padded)]
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
   const uint32_t seed_s = p.seed_s + salt, seed_2 = p.seed_2 + salt;
   const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
   const float* __restrict__ gx = p.x + (int64_t)g * N * H;
-  float* __restrict__ gout = p.out + (int64_t)g * N * H;
+  float* __restrict__ gout = p.out ? p.out + (int64_t)g * N * H : nullptr;
 
   float* sadj = smem;
   float* s_sp = smem + (p.adj_in_smem ? (size_t)N * NP : 0);
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
     }
     float* orow = gout + (int64_t)i * H;
     if (vecH) {
+      __nv_bfloat16* prow = p.out_p ? p.out_p + ((int64_t)g * N + i) * p.ld_p : nullptr;
 #pragma unroll
       for (int u = 0; u < MAX_QUADS_PER_LANE; ++u) {
         const int q = lane + u * 32;
@@ -217,8 +223,16 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
             const float4 o = *(reinterpret_cast<const float4*>(orow) + q);
             v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
           }
-          *(reinterpret_cast<float4*>(orow) + q) = v;
+          if (gout) *(reinterpret_cast<float4*>(orow) + q) = v;
+          if (prow) {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            planes_store4(prow + q * 4, p.ps_p, p.np_p, vv);
+          }
         }
+      }
+      if (prow && (H & 7) && lane == 0) {
+        const float vv[4] = {p.pad_one ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
+        planes_store4(prow + H, p.ps_p, p.np_p, vv);
       }
     } else {
 #pragma unroll
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
 
   const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
   const float* __restrict__ gx = p.x + (int64_t)g * N * H;
-  float* __restrict__ gout = p.out + (int64_t)g * N * H;
+  float* __restrict__ gout = p.out ? p.out + (int64_t)g * N * H : nullptr;
   const bool last_ok = (lane + (NQ - 1) * 32) < HQ;   // does this lane own a quad in the last (partial) group?
   const int nchunks = (N + 31) >> 5;
 
@@ -473,6 +487,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
       }
     }
     float4* orow = reinterpret_cast<float4*>(gout + (int64_t)i * H) + lane;
+    __nv_bfloat16* prow = p.out_p ? p.out_p + ((int64_t)g * N + i) * p.ld_p : nullptr;
 #pragma unroll
     for (int u = 0; u < NQ; ++u) {
       if (u < NQ - 1 || last_ok) {
@@ -481,8 +496,16 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
           const float4 o = orow[u * 32];
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
-        orow[u * 32] = v;
+        if (gout) orow[u * 32] = v;
+        if (prow) {
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          planes_store4(prow + (lane + u * 32) * 4, p.ps_p, p.np_p, vv);
+        }
       }
+    }
+    if (prow && (H & 7) && lane == 0) {
+      const float vv[4] = {p.pad_one ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
+      planes_store4(prow + H, p.ps_p, p.np_p, vv);
     }
   }
 }
@@ -810,6 +833,12 @@ __global__ void __launch_bounds__(GRAPH_THREADS) gsl_mask_adj_kernel(const float
 static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char* name) {
   GETB_REQUIRE(p.G >= 0 && p.N > 0 && p.H > 0, "%s: bad sizes G=%d N=%d H=%d", name, p.G, p.N, p.H);
   GETB_REQUIRE(p.H <= 32 * 4 * MAX_QUADS_PER_LANE, "%s: H=%d exceeds %d", name, p.H, 32 * 4 * MAX_QUADS_PER_LANE);
+  GETB_REQUIRE(p.out || p.out_p, "%s: no output", name);
+  GETB_REQUIRE(!p.accumulate || p.out, "%s: accumulate needs the fp32 output", name);
+  if (p.out_p)
+    GETB_REQUIRE((p.H % 4) == 0 && aligned16(p.x) && (!p.out || aligned16(p.out)) && (((uintptr_t)p.out_p) & 7u) == 0 &&
+                     (p.ld_p % 4) == 0 && (p.ps_p % 4) == 0 && p.np_p >= 1 && p.np_p <= 3 && p.ld_p >= ((p.H + 7) & ~7),
+                 "%s: plane output needs H %% 4 == 0 and aligned tensors", name);
   if (p.G == 0) return 0;
   {
     // experimental path (GET_B200_GRAPH_CLUSTER=1): 2-CTA cluster per graph, feature columns split between the CTAs
@@ -821,7 +850,7 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
       const char* e = getenv("GET_B200_GRAPH_CLUSTER");
       use_cluster = e ? atoi(e) : 0;   // measured slower than the single-CTA path on B200 (profiles/): opt-in only
     }
-    const bool okc = use_cluster && (p.H % 4) == 0 && hq >= 2 && (hq + 1) / 2 <= 64 && (p.N % 2) == 0 && p.N <= GS_MAX_N &&
+    const bool okc = use_cluster && !p.out_p && p.out && (p.H % 4) == 0 && hq >= 2 && (hq + 1) / 2 <= 64 && (p.N % 2) == 0 && p.N <= GS_MAX_N &&
                      aligned16(p.adj) && aligned16(p.x) && aligned16(p.out) && (!fused || aligned16(p.wp)) &&
                      need_c <= GS_SMEM_LIMIT && p.G <= (1 << 29);
     if (okc) {
@@ -845,7 +874,7 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
     const size_t need = ((size_t)p.N * p.H + 2 * (size_t)p.N * p.N + 4 * (size_t)p.N) * sizeof(float) +
                         (((size_t)p.N + 15) & ~(size_t)15) + (GS_CHUNKS + 1) * sizeof(uint64_t);
     const bool ok = (p.H % 4) == 0 && p.H <= 128 * GS_MAX_QUADS && (p.N % 2) == 0 && p.N <= GS_MAX_N && aligned16(p.adj) &&
-                    aligned16(p.x) && aligned16(p.out) && (!fused || aligned16(p.wp)) && need <= GS_SMEM_LIMIT;
+                    aligned16(p.x) && (!p.out || aligned16(p.out)) && (!fused || aligned16(p.wp)) && need <= GS_SMEM_LIMIT;
     if (ok) {
       const int nq = (p.H / 4 + 31) / 32;
       GraphSmemFn fn = graph_smem_fn(fused, nq);
@@ -915,6 +944,37 @@ extern "C" int get_gsl_fused_f32(const float* adj, const float* F, const float* 
   p.seed_s = seed_scorer; p.seed_2 = seed_layer2; p.salt = dropout_salt_ptr();
   p.score = score; p.keep_out = keep;
   return launch_graph(p, true, (cudaStream_t)stream, "get_gsl_fused_f32");
+}
+
+extern "C" int get_graph_aggregate_bp(const float* adj, const float* x, const uint8_t* keep, float* out, void* planes,
+                                      int64_t ld_p, int64_t plane_stride, int nplanes, int pad_one, int G, int N, int H,
+                                      int transpose, int accumulate, void* stream) {
+  GETB_REQUIRE(adj && x && (out || planes), "get_graph_aggregate_bp: null pointer");
+  GraphParams p;
+  memset(&p, 0, sizeof(p));
+  p.adj = adj; p.x = x; p.keep_in = keep; p.out = out;
+  p.out_p = reinterpret_cast<__nv_bfloat16*>(planes); p.ld_p = ld_p; p.ps_p = plane_stride; p.np_p = nplanes; p.pad_one = pad_one;
+  p.G = G; p.N = N; p.H = H; p.transpose = transpose; p.accumulate = accumulate;
+  return launch_graph(p, false, (cudaStream_t)stream, "get_graph_aggregate_bp");
+}
+
+extern "C" int get_gsl_fused_bp(const float* adj, const float* F, const float* wp, const float* gate, int G, int N, int H,
+                                int k, float drop_p, uint32_t seed_scorer, uint32_t seed_layer2, float* score, uint8_t* keep,
+                                float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream) {
+  GETB_REQUIRE(adj && F && wp && gate && keep && (out || planes), "get_gsl_fused_bp: null pointer");
+  GETB_REQUIRE(k >= 0 && k <= N, "get_gsl_fused_bp: k=%d out of [0,%d]", k, N);
+  GETB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "get_gsl_fused_bp: dropout probability must be in [0,1)");
+  GETB_REQUIRE(aligned16(wp) || (H & 3), "get_gsl_fused_bp: wp must be 16-byte aligned");
+  GraphParams p;
+  memset(&p, 0, sizeof(p));
+  p.adj = adj; p.x = F; p.out = out; p.G = G; p.N = N; p.H = H;
+  p.out_p = reinterpret_cast<__nv_bfloat16*>(planes); p.ld_p = ld_p; p.ps_p = plane_stride; p.np_p = nplanes;
+  p.wp = wp; p.gate = gate; p.k = k;
+  p.thr = drop_p > 0.f ? drop_threshold(drop_p) : 0;
+  p.scale = 1.0f / (1.0f - drop_p);
+  p.seed_s = seed_scorer; p.seed_2 = seed_layer2; p.salt = dropout_salt_ptr();
+  p.score = score; p.keep_out = keep;
+  return launch_graph(p, true, (cudaStream_t)stream, "get_gsl_fused_bp");
 }
 
 extern "C" int get_gsl_mask_adj_f32(const float* adj, const float* score, int G, int N, int k, float* adj_out,

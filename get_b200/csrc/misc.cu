@@ -4,6 +4,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace getb {
 
@@ -183,6 +184,59 @@ __global__ void __launch_bounds__(256) rows_gather_dropout_kernel(const float* _
   }
 }
 
+// ---- plane-emitting variants (operands of the bf16-plane tensor-core GEMM, see get_gemm_bp) ----------------------------
+// GGNN backward element-wise stage writing the gate gradients as bf16 planes: dz' -> column block col_z, dh' -> col_h of
+// the (M, ld_g) gate-gradient plane buffer [dz' | dr' | dh'] (pad columns up to a multiple of 8 written as zeros);
+// dx (fp32) = dout * (1 - z).
+__global__ void __launch_bounds__(256) ggnn_gate_bwd_bp_kernel(const float* __restrict__ dout, const float* __restrict__ z,
+                                                               const float* __restrict__ h, const float* __restrict__ x,
+                                                               int M, int H, __nv_bfloat16* __restrict__ dg, int64_t ld_g,
+                                                               int64_t plane_stride, int nplanes, int col_z, int col_h,
+                                                               float* __restrict__ dx) {
+  const int hq = ((H + 7) & ~7) >> 2;        // quads per row including the padding quad(s)
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (int64_t)M * hq) return;
+  const int m = (int)(q / hq), c = (int)(q % hq) * 4;
+  float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < H) {
+    const int64_t i = (int64_t)m * H + c;
+    const float4 d = *reinterpret_cast<const float4*>(dout + i), zz = *reinterpret_cast<const float4*>(z + i);
+    const float4 hh = *reinterpret_cast<const float4*>(h + i), xx = *reinterpret_cast<const float4*>(x + i);
+    o0[0] = d.x * zz.x * (1.0f - hh.x * hh.x); o0[1] = d.y * zz.y * (1.0f - hh.y * hh.y);
+    o0[2] = d.z * zz.z * (1.0f - hh.z * hh.z); o0[3] = d.w * zz.w * (1.0f - hh.w * hh.w);
+    o1[0] = d.x * (hh.x - xx.x) * zz.x * (1.0f - zz.x); o1[1] = d.y * (hh.y - xx.y) * zz.y * (1.0f - zz.y);
+    o1[2] = d.z * (hh.z - xx.z) * zz.z * (1.0f - zz.z); o1[3] = d.w * (hh.w - xx.w) * zz.w * (1.0f - zz.w);
+    *reinterpret_cast<float4*>(dx + i) = make_float4(d.x * (1.0f - zz.x), d.y * (1.0f - zz.y), d.z * (1.0f - zz.z), d.w * (1.0f - zz.w));
+  }
+  planes_store4(dg + (int64_t)m * ld_g + col_h + c, plane_stride, nplanes, o0);
+  planes_store4(dg + (int64_t)m * ld_g + col_z + c, plane_stride, nplanes, o1);
+}
+
+// out planes[r, :] = dropout(src[idx ? idx[r] : r, :]) (embedding gather gbss.py:100,150 + nn.Dropout wrapper.py:189-190),
+// mask index r*W + c; pad columns W..round_up(W,8)-1 written as zeros
+__global__ void __launch_bounds__(128) rows_gather_dropout_bp_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                                     const int64_t* __restrict__ idx, int R, int W,
+                                                                     uint32_t thr, float scale, uint32_t seed,
+                                                                     const uint32_t* __restrict__ salt,
+                                                                     __nv_bfloat16* __restrict__ out, int64_t ld_out,
+                                                                     int64_t plane_stride, int nplanes) {
+  const uint32_t sd = seed + (thr ? __ldg(salt) : 0u);
+  const int wq = ((W + 7) & ~7) >> 2;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const float* s = src + (idx ? idx[r] : (int64_t)r) * ld_src;
+    __nv_bfloat16* d = out + (int64_t)r * ld_out;
+    for (int q = threadIdx.x; q < wq; q += blockDim.x) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (q * 4 < W) {
+        float4 f = __ldg(reinterpret_cast<const float4*>(s) + q);
+        if (thr) drop_apply4(sd, (uint64_t)r * (uint64_t)W + (uint64_t)q * 4, thr, scale, f);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      }
+      planes_store4(d + q * 4, plane_stride, nplanes, v);
+    }
+  }
+}
+
 // ---- mean cross-entropy + dlogits (reference losses.py:29-32); one warp, B is a few hundred at most
 __global__ void __launch_bounds__(32) cross_entropy_kernel(const float* __restrict__ logits,
                                                            const int64_t* __restrict__ labels, int B, int C,
@@ -337,6 +391,39 @@ extern "C" int get_rows_gather_dropout_f32(const float* src, int64_t ld_src, con
   rows_gather_dropout_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, ld_src, idx, R, W, p > 0.f ? drop_threshold(p) : 0u,
                                                                     1.0f / (1.0f - p), seed, dropout_salt_ptr(), out, ld_out, vec);
   GETB_CHECK_LAUNCH("get_rows_gather_dropout_f32");
+  return 0;
+}
+
+extern "C" int get_ggnn_gate_bwd_bp(const float* dout, const float* z, const float* h, const float* x, int M, int H, void* dg,
+                                    int64_t ld_g, int64_t plane_stride, int nplanes, int col_z, int col_h, float* dx,
+                                    void* stream) {
+  GETB_REQUIRE(dout && z && h && x && dg && dx, "get_ggnn_gate_bwd_bp: null pointer");
+  GETB_REQUIRE((H % 4) == 0 && (ld_g % 4) == 0 && (plane_stride % 4) == 0 && (col_z % 4) == 0 && (col_h % 4) == 0 &&
+                   nplanes >= 1 && nplanes <= 3 && aligned16(dout) && aligned16(z) && aligned16(h) && aligned16(x) &&
+                   aligned16(dx) && (((uintptr_t)dg) & 7u) == 0,
+               "get_ggnn_gate_bwd_bp: H %% 4, alignment or plane count");
+  if (M <= 0 || H <= 0) return 0;
+  const int64_t nq = (int64_t)M * (((H + 7) & ~7) / 4);
+  ggnn_gate_bwd_bp_kernel<<<ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(dout, z, h, x, M, H, reinterpret_cast<__nv_bfloat16*>(dg),
+                                                                              ld_g, plane_stride, nplanes, col_z, col_h, dx);
+  GETB_CHECK_LAUNCH("get_ggnn_gate_bwd_bp");
+  return 0;
+}
+
+extern "C" int get_rows_gather_dropout_bp(const float* src, int64_t ld_src, const int64_t* idx, int R, int W, float p,
+                                          uint32_t seed, void* planes, int64_t ld_out, int64_t plane_stride, int nplanes,
+                                          void* stream) {
+  GETB_REQUIRE(src && planes && p >= 0.f && p < 1.f, "get_rows_gather_dropout_bp: bad arguments");
+  GETB_REQUIRE((W % 4) == 0 && (ld_src % 4) == 0 && (ld_out % 4) == 0 && (plane_stride % 4) == 0 && aligned16(src) &&
+                   (((uintptr_t)planes) & 7u) == 0 && nplanes >= 1 && nplanes <= 3 && ld_out >= ((W + 7) & ~7),
+               "get_rows_gather_dropout_bp: W %% 4, alignment or plane count");
+  if (R <= 0 || W <= 0) return 0;
+  const int grid = R < 148 * 16 ? R : 148 * 16;
+  rows_gather_dropout_bp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, ld_src, idx, R, W, p > 0.f ? drop_threshold(p) : 0u,
+                                                                       1.0f / (1.0f - p), seed, dropout_salt_ptr(),
+                                                                       reinterpret_cast<__nv_bfloat16*>(planes), ld_out,
+                                                                       plane_stride, nplanes);
+  GETB_CHECK_LAUNCH("get_rows_gather_dropout_bp");
   return 0;
 }
 

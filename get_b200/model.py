@@ -152,10 +152,12 @@ class Graph_basedSemantiStructure(nn.Module):
         blk_seeds = None
         if seeds:
             blk_seeds = (seeds.get("feat_prop1", 0), seeds.get("word_scorer1", 0), seeds.get("feat_prop2", 0))
+        npl = ops.gemm_mode(False)      # planes of the block output: operand of the word-attention projection
         if emb_fused:
-            doc_out = self.ggnn_with_gsl(doc_adj, table=self.embedding.weight, ids=doc, seeds=blk_seeds)
+            doc_out, doc_planes = self.ggnn_with_gsl(doc_adj, table=self.embedding.weight, ids=doc, seeds=blk_seeds,
+                                                     out_planes=npl)
         else:
-            doc_out = self.ggnn_with_gsl(doc_adj, self.embedding(doc.long()), seeds=blk_seeds)
+            doc_out, doc_planes = self.ggnn_with_gsl(doc_adj, self.embedding(doc.long()), seeds=blk_seeds, out_planes=npl)
 
         if fork:
             cur.wait_stream(self._side_stream)
@@ -163,7 +165,7 @@ class Graph_basedSemantiStructure(nn.Module):
         query_repr = ops.SegmentExpandFn.apply(q_claim, seg, offsets)                # (B1, H)
 
         # word-level attention (gbss.py:110, 173-193)
-        avg, word_att = self.self_att_word(query_repr, doc_out, doc >= 1)
+        avg, word_att = self.self_att_word(query_repr, doc_out, doc >= 1, right_planes=doc_planes)
         avg = torch.flatten(avg, start_dim=1)                                        # (B1, H*heads), index d*heads+head
 
         # evidence-level attention (gbss.py:113-119, 195-221)

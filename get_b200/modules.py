@@ -62,15 +62,19 @@ class GGNN(nn.Module):
                 self.linearh0.linear.weight, self.linearh0.linear.bias,
                 self.linearh1.linear.weight, self.linearh1.linear.bias)
 
-    def forward(self, adj, x=None, *, table=None, ids=None, keep=None, pre_agg=None, seed=None, exact_fwd=False):
+    def forward(self, adj, x=None, *, table=None, ids=None, keep=None, pre_agg=None, seed=None, exact_fwd=False,
+                out_planes=0):
         """Reference call: forward(adj, x). Extensions used inside this package: (table, ids) = frozen embedding
         table + token ids instead of x (gather fused into the projection), keep / pre_agg from the GSL kernel,
-        explicit dropout seed (tests)."""
+        explicit dropout seed (tests), out_planes > 0: also return the bf16 planes of the output (the operand of the
+        next tensor-core contraction) -> (out, planes)."""
         p = self.p_drop if self.training else 0.0
         if p > 0 and seed is None:
             seed = ops.new_seed()
         adj = adj.float()
-        return ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params(), exact_fwd=exact_fwd)
+        out, op = ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params(), exact_fwd=exact_fwd,
+                                 out_planes=out_planes)
+        return (out, op) if out_planes else out
 
 
 class GSL(nn.Module):
@@ -110,7 +114,7 @@ class GGNN_with_GSL(nn.Module):
             s.linearh0.linear.weight, s.linearh0.linear.bias, s.linearh1.linear.weight, s.linearh1.linear.bias)])
         return wp, gate
 
-    def forward(self, adj, feat=None, *, table=None, ids=None, seeds=None, want_score=True):
+    def forward(self, adj, feat=None, *, table=None, ids=None, seeds=None, want_score=True, out_planes=0):
         adj = adj.float().contiguous()
         n = adj.shape[-1]
         k = int(self.gsl1.rate * n)
@@ -121,10 +125,15 @@ class GGNN_with_GSL(nn.Module):
         wp, gate = self._scorer_params()
         ps = self.word_scorer1.p_drop if self.training else 0.0
         assert ps == p or ps == 0 or p == 0, "scorer / layer-2 dropout rates are the same value in the reference"
+        # the refined aggregation leaves the fused kernel as bf16 planes: it is only ever the operand of feat_prop2's
+        # projection (wrapper.py:191-192, by linearity of the bias-free proj)
+        G, N, H1 = f1.shape
+        tc = ops.layer_uses_tc(G * N, self.feat_prop2.out_features, H1)
         score, keep, agg = ops.gsl_fused(adj, f1.detach(), wp, gate, k, drop_p=max(p, ps), seed_scorer=seeds[1],
-                                         seed_layer2=seeds[2], want_score=want_score)
+                                         seed_layer2=seeds[2], want_score=want_score,
+                                         planes_n=ops.gemm_mode(False) if tc else 0)
         self.last_keep, self.last_score = keep, score
-        return self.feat_prop2(adj, f1, keep=keep, pre_agg=agg, seed=seeds[2])
+        return self.feat_prop2(adj, f1, keep=keep, pre_agg=agg.t if tc else agg, seed=seeds[2], out_planes=out_planes)
 
 
 class ConcatNotEqualSelfAtt(nn.Module):
@@ -138,11 +147,14 @@ class ConcatNotEqualSelfAtt(nn.Module):
         self.linear1 = nn.Linear(inp_dim, out_dim, bias=False)
         self.linear2 = nn.Linear(out_dim, num_heads, bias=False)
 
-    def forward(self, left: torch.Tensor, right: torch.Tensor, mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward(self, left: torch.Tensor, right: torch.Tensor, mask: torch.Tensor,
+                right_planes: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Reference call: forward(left, right, mask). right_planes: bf16 planes of `right` when the producing kernel
+        already wrote them (package-internal)."""
         assert left.size(0) == right.size(0), "Must same dimensions"
         assert len(left.size()) == 2 and len(right.size()) == 3
         assert self.inp_dim == (left.size(-1) + right.size(-1))  # due to concat
-        return ops.concat_att(left, right, mask, self.linear1.weight, self.linear2.weight)
+        return ops.concat_att(left, right, mask, self.linear1.weight, self.linear2.weight, right_planes)
 
 
 class MultiHeadSelfAttentionICLR2017Extend(nn.Module):

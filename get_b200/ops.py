@@ -11,9 +11,10 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from . import _lib
-from ._lib import (EPI_DGATE_R, EPI_DROPOUT_OUT, EPI_SIGMOID, EPI_STORE, EPI_TANH, EPI_TANH_BLEND,
-                   EPI_TANH_ROWGROUP, GemmDesc)
+from . import _lib, planes
+from ._lib import (BPE_DGATE_R, BPE_STORE, BPE_TANH, BPE_TANH_BLEND, BPE_TANH_ROWGROUP, BPE_ZR, EPI_DGATE_R,
+                   EPI_DROPOUT_OUT, EPI_SIGMOID, EPI_STORE, EPI_TANH, EPI_TANH_BLEND, EPI_TANH_ROWGROUP, GemmDesc)
+from .planes import Planes, alloc_planes, gemm_bp, get_pack, pack_of, round_up, to_planes, wgrad_bp
 
 _SM_COUNT = 148
 # bench.py sets this to a list to time the fused GSL kernel with CUDA events on its launch stream:
@@ -70,35 +71,46 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
-# Precision class of the contractions that do NOT feed the GSL top-k:
-#   "fp32" (default): error-compensated 3xTF32 everywhere -- the 1e-4 parity class (BASELINE.json configs[1]);
-#   "fast": a single tf32 tensor-core pass for everything except the forward of feat_prop1 (whose output decides the
-#           kept node set and therefore stays 3xTF32) -- the 1e-2 parity class of BASELINE.json configs[2].
+# Precision class of the contractions that do NOT feed the GSL top-k (the forward of feat_prop1 decides the kept node set
+# and runs in the fp32-exact class in every mode):
+#   "fp32"  (default): 16-bit operands (two bf16 planes, three tensor-core products; relative error ~1e-5) -- the 1e-4
+#           parity class of BASELINE.json configs[1];
+#   "fp32x": the fp32-exact class everywhere (three planes, six products);
+#   "bf16":  plain bf16 operands, fp32 accumulation -- the 1e-2 parity class of BASELINE.json configs[2] ("fast" = alias).
 PRECISION = os.environ.get("GET_B200_PRECISION", "fp32")
 
 
 def set_precision(mode: str):
     global PRECISION
-    assert mode in ("fp32", "fast"), mode
+    if mode == "fast":
+        mode = "bf16"
+    assert mode in ("fp32", "fp32x", "bf16"), mode
     PRECISION = mode
 
 
-# Tensor-core (tcgen05, 3xTF32) path for the weight GEMMs; GET_B200_TC=0 forces the exact SIMT path everywhere.
+def gemm_mode(exact: bool = False) -> int:
+    """Plane-product mode of get_gemm_bp for the current precision class (3 = fp32-exact, 2 = 16-bit operands, 1 = bf16)."""
+    if exact or PRECISION == "fp32x":
+        return 3
+    return 2 if PRECISION == "fp32" else 1
+
+
+# Tensor-core (tcgen05, bf16 planes) path for the large contractions; GET_B200_TC=0 forces the exact SIMT path everywhere
+# (debugging / A-B comparisons only).
 TC_ENABLED = os.environ.get("GET_B200_TC", "1") != "0"
 DEBUG_TC_REPORT = False      # tests: record in LAST_GEMM_USED_TC whether the last gemm() ran on the tcgen05 path
 LAST_GEMM_USED_TC = None
-_split_cache = {}
-_SPLIT_CACHE_MAX = 512
 
-
-_split_epoch = 0
+# Weight gradients written straight into caller-owned buffers (the flat gradient bucket of get_b200.ddp): maps
+# parameter data_ptr -> fp32 view of the same shape. When a parameter is registered here the backward passes ACCUMULATE
+# into the view (the owner zeroes the bucket at the start of a step) and return no gradient for it.
+GRAD_SINK = {}
 
 
 def weights_updated(*_args, **_kwargs):
-    """Invalidate every cached weight split. Registered as a global optimizer post-step hook: fused / foreach optimizer
+    """Invalidate every packed weight. Registered as a global optimizer post-step hook: fused / foreach optimizer
     kernels update parameters without moving their version counters, so the counter alone cannot be trusted."""
-    global _split_epoch
-    _split_epoch += 1
+    planes.weights_updated()
 
 
 try:
@@ -110,104 +122,18 @@ except Exception:      # very old torch: callers must invoke ops.weights_updated
 
 def begin_step_capture():
     """Call at the head of a training step that is being captured into a CUDA graph: the weights differ at every
-    replay, so every weight must be re-split INSIDE the captured step (first use), whatever its version counter says."""
-    global _split_epoch
-    _split_epoch += 1
-
-
-_split_table = None        # (device uint8 tensor holding get_split_job[], n_jobs, total_blocks, keys) or None when stale
-
-
-def _run_single_split(b, hi, lo):
-    lib = _lib.load()
-    N, K = b.shape
-    _lib.check(lib.get_split_tf32_f32(b.data_ptr(), b.stride(0), b.stride(1), N, K, hi.data_ptr(), lo.data_ptr(),
-                                      hi.stride(0), _stream()), "get_split_tf32_f32")
+    replay, so every weight must be re-packed INSIDE the captured step (first use), whatever its version counter says."""
+    planes.begin_step_capture()
 
 
 def prepare_split_table():
-    """(Re)build the device job table covering every cached weight. Copies host memory to the device, so it must run
-    OUTSIDE a stream capture (CapturedTrainStep calls it right before capturing)."""
-    global _split_table
-    if _split_table is not None or not _split_cache:
-        return
-    keys = list(_split_cache.keys())
-    jobs = (_lib.SplitJob * len(keys))()
-    blocks = 0
-    for j, key in enumerate(keys):
-        ent = _split_cache[key]
-        ptr, shape, strides = key
-        jobs[j].src, jobs[j].ld_r, jobs[j].ld_c = ptr, strides[0], strides[1]
-        jobs[j].rows, jobs[j].cols = shape
-        jobs[j].hi, jobs[j].lo, jobs[j].ld_out = ent[1].data_ptr(), ent[2].data_ptr(), ent[1].stride(0)
-        jobs[j].first_block = blocks
-        blocks += (shape[0] * shape[1] + 255) // 256
-    raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
-    _split_table = (raw.to(ent[1].device), len(keys), blocks, keys)
+    """(Re)build the device job table covering every packed weight (host -> device copy: outside stream captures only)."""
+    planes.prepare_pack_table()
 
 
 def refresh_weight_splits() -> bool:
-    """Bring every cached weight split up to date NOW, on the current stream (one launch). Returns True when the cache is
-    populated and current afterwards -- the condition under which independent branches of the model may run on side
-    streams without racing on the lazily refreshed splits."""
-    global _split_table
-    if not _split_cache:
-        return False
-    stale = any(e[0][1] != _split_epoch for e in _split_cache.values())
-    if stale:
-        if _split_table is None:
-            if torch.cuda.is_current_stream_capturing():
-                return False
-            prepare_split_table()
-        tab, n, blocks, keys = _split_table
-        _lib.check(_lib.load().get_split_tf32_multi_f32(tab.data_ptr(), n, blocks, _stream()), "get_split_tf32_multi_f32")
-        for k2 in keys:
-            e2 = _split_cache.get(k2)
-            if e2 is not None:
-                e2[0] = (e2[0][0], _split_epoch)
-    return all(e[0][1] == _split_epoch for e in _split_cache.values())
-
-
-def split_weight(b: torch.Tensor):
-    """(hi, lo) k-contiguous TF32 split of a weight view b (logical (N, K), any strides), cached per
-    (storage address, shape, strides). Refreshed when the weights change: the optimizer post-step hook / a captured step
-    bump the epoch and the FIRST weight asked for afterwards refreshes every cached split in one launch; a moved version
-    counter (in-place edit of one tensor) refreshes that tensor alone."""
-    global _split_table
-    key = (b.data_ptr(), tuple(b.shape), tuple(b.stride()))
-    ent = _split_cache.get(key)
-    if ent is not None and ent[0] == (b._version, _split_epoch):
-        return ent[1], ent[2]
-    _chk_f32(b, "B")
-    if ent is None:
-        N, K = b.shape
-        ldo = (K + 3) // 4 * 4
-        hi = torch.zeros((N, ldo), dtype=torch.float32, device=b.device)
-        lo = torch.zeros((N, ldo), dtype=torch.float32, device=b.device)
-        _run_single_split(b, hi, lo)
-        # the entry pins the source storage: while it is cached the allocator cannot hand the same address to another
-        # tensor, so (address, shape, strides) identifies the weight
-        _split_cache[key] = [(b._version, _split_epoch), hi, lo, b.untyped_storage()]
-        if len(_split_cache) > _SPLIT_CACHE_MAX:
-            _split_cache.pop(next(iter(_split_cache)))
-        _split_table = None              # the job table no longer matches the cache
-        return hi, lo
-    if ent[0][1] != _split_epoch:
-        capturing = torch.cuda.is_current_stream_capturing()
-        if _split_table is None and not capturing:
-            prepare_split_table()
-        if _split_table is not None:
-            tab, n, blocks, keys = _split_table
-            _lib.check(_lib.load().get_split_tf32_multi_f32(tab.data_ptr(), n, blocks, _stream()), "get_split_tf32_multi_f32")
-            for k2 in keys:
-                e2 = _split_cache.get(k2)
-                if e2 is not None:
-                    e2[0] = (e2[0][0], _split_epoch)
-            if ent[0][0] == b._version:
-                return ent[1], ent[2]
-    _run_single_split(b, ent[1], ent[2])
-    ent[0] = (b._version, _split_epoch)
-    return ent[1], ent[2]
+    """Bring every packed weight up to date NOW on the current stream (one launch); True when all packs are current."""
+    return planes.refresh_packs()
 
 
 def dropout_salt_set(value: int):
@@ -238,22 +164,100 @@ def rows_gather_dropout(src: torch.Tensor, idx: Optional[torch.Tensor], rows: in
     return out
 
 
+def rows_gather_dropout_planes(src: torch.Tensor, idx: Optional[torch.Tensor], rows: int, p: float, seed: int,
+                               nplanes: int) -> Planes:
+    """Planes of dropout(src[idx]) (idx int64 or None = identity): the A operand of a GGNN input projection."""
+    lib = _lib.load()
+    _chk_f32(src, "src")
+    assert src.dim() == 2 and src.stride(1) == 1
+    W = src.shape[1]
+    out = alloc_planes(nplanes, rows, W, src.device)
+    if idx is not None:
+        assert idx.dtype == torch.int64 and idx.is_cuda and idx.is_contiguous() and idx.numel() == rows
+    _lib.check(lib.get_rows_gather_dropout_bp(src.data_ptr(), src.stride(0), _ptr(idx), rows, W, float(p), seed & 0xFFFFFFFF,
+                                              out.ptr, out.ld, out.plane_stride, nplanes, _stream()),
+               "get_rows_gather_dropout_bp")
+    return out
+
+
 def new_seed() -> int:
     """32-bit dropout seed drawn from torch's CPU generator (follows torch.manual_seed)."""
     return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
+def _as_rowmajor_2d(t: torch.Tensor):
+    """(tensor with unit column stride, transposed?) for a 2-D fp32 view with one unit stride."""
+    assert t.dim() == 2
+    if t.stride(1) == 1 or t.shape[1] == 1:
+        return t, False
+    if t.stride(0) == 1 or t.shape[0] == 1:
+        return t.t(), True
+    raise RuntimeError("get_b200.gemm: operand has no unit stride %s" % (t.stride(),))
+
+
+_BPE_OF = {EPI_STORE: BPE_STORE, EPI_TANH: BPE_TANH, EPI_TANH_ROWGROUP: BPE_TANH_ROWGROUP, EPI_DROPOUT_OUT: BPE_STORE}
+
+
+def _gemm_tc(segments, out, epilogue, bias0, bias1, aux0, group_rows, accumulate, drop_out_p, drop_out_seed, presplit,
+             exact, planes_out=None):
+    """The tensor-core route of gemm(): fp32 A operands are converted to planes on the fly (callers on the hot path hand
+    over Planes written by the producing kernel instead), weights come from the pack cache."""
+    M, N = out.shape
+    mode = gemm_mode(exact)
+    if presplit:
+        segs = []
+        bias = None
+        for s_i, (a, b) in enumerate(segments):
+            ap = a if isinstance(a, Planes) else to_planes(_rows_view(a), mode)
+            pk = pack_of(b, bias0, bias1) if (s_i == 0 and bias0 is not None) else pack_of(b)
+            if s_i == 0 and bias0 is not None:
+                bias = pk.bias
+            segs.append((ap, pk.planes, b.shape[1]))
+        gemm_bp(segs, M, N, mode=mode, epilogue=_BPE_OF[epilogue], C=out, bias=bias, aux0=aux0, group_rows=group_rows,
+                accumulate=accumulate, drop_out=(drop_out_p, drop_out_seed) if epilogue == EPI_DROPOUT_OUT else None,
+                planes_out=planes_out)
+        return
+    # activation x activation (weight gradient): both operands are transposed views of (K, .) row-major matrices
+    assert len(segments) == 1 and epilogue == EPI_STORE and bias0 is None
+    a, b = segments[0]
+    ar, at = (a, True) if isinstance(a, Planes) else _as_rowmajor_2d(a)
+    br, bt = (b, True) if isinstance(b, Planes) else _as_rowmajor_2d(b)
+    assert at and bt, "weight-gradient contraction expects (K, .) row-major operands passed as .t() views"
+    ap = ar if isinstance(ar, Planes) else to_planes(ar, mode)
+    bp_ = br if isinstance(br, Planes) else to_planes(br, mode)
+    K = ap.rows
+    wgrad_bp(ap.T() if ap.trans == 0 else ap, bp_.T() if bp_.trans == 0 else bp_, M, N, K, mode,
+             [(out, 0, M, 0, N)], accumulate=accumulate)
+
+
+def _rows_view(a: torch.Tensor) -> torch.Tensor:
+    r, t = _as_rowmajor_2d(a)
+    return a.contiguous() if t else r
 
 
 def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tensor, *, epilogue: int = EPI_STORE,
          bias0=None, bias1=None, aux0=None, aux1=None, out1=None, group_rows: int = 0, alpha: float = 1.0,
          accumulate: bool = False, rowidx: Optional[torch.Tensor] = None, drop_p: float = 0.0, drop_seed: int = 0,
          drop_cols: int = 0, drop_out_p: float = 0.0, drop_out_seed: int = 0, split_k: Optional[int] = None,
-         tc: bool = False, tc_n_tiles: int = 0, presplit: bool = True, exact: bool = False):
+         tc: bool = False, presplit: bool = True, exact: bool = False, planes_out: Optional[Planes] = None):
     """out[m,n] = epilogue(sum_s A_s[m,:] . B_s[n,:]); A_s logical (M,K_s), B_s logical (N,K_s).
-    tc=True: offer the tcgen05 path. presplit=True (every B_s is a weight): hand over the cached hi/lo split of the
-    weights; presplit=False (B_s are activations, e.g. weight gradients): the kernel splits both operands itself.
-    exact=True pins the contraction to the fp32-accurate path even when PRECISION == "fast" (the GSL top-k chain)."""
+    tc=True: run on the tcgen05 plane GEMM when the shape allows it (M >= 128, N % 4 == 0, a store / tanh epilogue);
+    presplit=True: every B_s is a weight (packed planes come from the cache); presplit=False: both operands are
+    activations (a weight gradient). Otherwise (small / odd contractions: output MLP, per-claim projections) the exact
+    fp32 SIMT kernel runs. exact=True pins the contraction to the fp32-exact class (the GSL top-k chain)."""
     lib = _lib.load()
     M, N = out.shape
+    want_tc = (tc and TC_ENABLED and M >= 128 and N % 4 == 0 and N >= 8 and alpha == 1.0 and rowidx is None and drop_p == 0.0
+               and epilogue in _BPE_OF and aux1 is None and out1 is None and out.stride(1) == 1 and out.stride(0) % 4 == 0
+               and (not presplit or all(b.shape[1] >= 8 for _, b in segments)))
+    if DEBUG_TC_REPORT:
+        global LAST_GEMM_USED_TC
+        LAST_GEMM_USED_TC = 2 if want_tc else 0
+    if want_tc:
+        _gemm_tc(segments, out, epilogue, bias0, bias1, aux0, group_rows, accumulate, drop_out_p, drop_out_seed, presplit,
+                 exact, planes_out)
+        return out
+    assert planes_out is None
     d = GemmDesc()
     d.nseg = len(segments)
     ktiles = 0
@@ -283,54 +287,46 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
     d.group_rows = group_rows
     d.drop_p, d.drop_seed, d.drop_cols = drop_p, drop_seed & 0xFFFFFFFF, drop_cols
     d.drop_out_p, d.drop_out_seed = drop_out_p, drop_out_seed & 0xFFFFFFFF
-    want_tc = tc and TC_ENABLED and M >= 128
     if split_k is None:
         tiles = ((M + 127) // 128) * ((N + 63) // 64)
         split_k = 1
-        if want_tc and not presplit:
-            # activation x activation on the tensor cores: (128 x <=160) tiles, k blocks of 32, one CTA per work item
-            tc_tiles = ((M + 127) // 128) * ((N + 159) // 160)
-            if tc_tiles < _SM_COUNT:
-                split_k = max(1, min(_SM_COUNT // tc_tiles, ktiles // 16))
-        elif not want_tc and tiles < _SM_COUNT and ktiles >= 16:
+        if tiles < _SM_COUNT and ktiles >= 16:
             split_k = max(1, min(ktiles // 8, (2 * _SM_COUNT + tiles - 1) // tiles))
     ws = None
     if split_k > 1:
         ws = torch.empty((split_k * M * N,), dtype=torch.float32, device=out.device)
         d.workspace = ws.data_ptr()
     d.split_k = split_k
-    if want_tc and (split_k <= 1 or not presplit):
-        if presplit:
-            keep_alive = []
-            for s, (a, b) in enumerate(segments):
-                hi, lo = split_weight(b)
-                keep_alive.append((hi, lo))
-                d.B_hi[s], d.B_lo[s], d.ld_split[s] = hi.data_ptr(), lo.data_ptr(), hi.stride(0)
-        d.tc_mode, d.tc_n_tiles = (2 if (PRECISION == "fast" and not exact) else 1), tc_n_tiles
-    if DEBUG_TC_REPORT:
-        global LAST_GEMM_USED_TC
-        LAST_GEMM_USED_TC = int(lib.get_gemm_f32_uses_tc(C.byref(d)))
     _lib.check(lib.get_gemm_f32(C.byref(d), _stream()), "get_gemm_f32")
     return out
 
 
-def graph_aggregate(adj, x, keep=None, out=None, transpose=False, accumulate=False):
+def graph_aggregate(adj, x, keep=None, out=None, transpose=False, accumulate=False, planes_out: Optional[Planes] = None,
+                    pad_one: bool = False, want_f32: bool = True):
+    """out[g] (+)= op(adj'[g]) @ x[g]; optionally also (or only, want_f32=False) as bf16 planes for the next contraction."""
     lib = _lib.load()
     _chk_f32(adj, "adj"); _chk_f32(x, "x")
     G, N, H = x.shape
     assert adj.shape == (G, N, N) and adj.is_contiguous() and x.is_contiguous()
-    if out is None:
+    if out is None and want_f32:
         assert not accumulate
         out = torch.empty_like(x)
     if keep is not None:
         assert keep.dtype == torch.uint8 and keep.shape == (G, N) and keep.is_contiguous()
-    _lib.check(lib.get_graph_aggregate_f32(adj.data_ptr(), x.data_ptr(), _ptr(keep), out.data_ptr(), G, N, H,
-                                           int(transpose), int(accumulate), _stream()), "get_graph_aggregate_f32")
+    if planes_out is None:
+        _lib.check(lib.get_graph_aggregate_f32(adj.data_ptr(), x.data_ptr(), _ptr(keep), out.data_ptr(), G, N, H,
+                                               int(transpose), int(accumulate), _stream()), "get_graph_aggregate_f32")
+    else:
+        assert planes_out.rows == G * N and planes_out.cols == H
+        _lib.check(lib.get_graph_aggregate_bp(adj.data_ptr(), x.data_ptr(), _ptr(keep), _ptr(out), planes_out.ptr, planes_out.ld,
+                                              planes_out.plane_stride, planes_out.nplanes, int(pad_one), G, N, H,
+                                              int(transpose), int(accumulate), _stream()), "get_graph_aggregate_bp")
     return out
 
 
-def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, want_score=True):
-    """Fused scorer -> top-k -> refined aggregation. Returns (score (G,N) | None, keep (G,N) uint8, out (G,N,H))."""
+def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, want_score=True, planes_n: int = 0):
+    """Fused scorer -> top-k -> refined aggregation. Returns (score (G,N) | None, keep (G,N) uint8, out): out is fp32
+    (G,N,H), or with planes_n > 0 the refined aggregation as bf16 Planes (G*N, H) for the layer-2 projection."""
     lib = _lib.load()
     _chk_f32(adj, "adj"); _chk_f32(feat, "feat"); _chk_f32(wp, "wp"); _chk_f32(gate, "gate")
     G, N, H = feat.shape
@@ -338,7 +334,7 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     assert wp.numel() == H and wp.is_contiguous() and gate.numel() == 12 and gate.is_contiguous()
     score = torch.empty((G, N), dtype=torch.float32, device=feat.device) if want_score else None
     keep = torch.empty((G, N), dtype=torch.uint8, device=feat.device)
-    out = torch.empty_like(feat)
+    out = alloc_planes(planes_n, G * N, H, feat.device) if planes_n else torch.empty_like(feat)
     if PROFILE_GSL_ARGS is not None:
         PROFILE_GSL_ARGS.append((adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF,
                                  seed_layer2 & 0xFFFFFFFF, score, keep, out))
@@ -346,23 +342,30 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(lib.get_gsl_fused_f32(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, int(k),
-                                     float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF,
-                                     _ptr(score), keep.data_ptr(), out.data_ptr(), _stream()), "get_gsl_fused_f32")
+    _gsl_launch(adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF, score, keep, out)
     if prof is not None:
         e1.record()
         prof.append((e0, e1, G))
     return score, keep, out
 
 
+def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out):
+    lib = _lib.load()
+    G, N, H = feat.shape
+    if isinstance(out, Planes):
+        _lib.check(lib.get_gsl_fused_bp(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k, drop_p, s1, s2,
+                                        _ptr(score), keep.data_ptr(), None, out.ptr, out.ld, out.plane_stride, out.nplanes,
+                                        _stream()), "get_gsl_fused_bp")
+    else:
+        _lib.check(lib.get_gsl_fused_f32(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k, drop_p, s1,
+                                         s2, _ptr(score), keep.data_ptr(), out.data_ptr(), _stream()), "get_gsl_fused_f32")
+
+
 def gsl_fused_replay(rec):
     """Re-issue one recorded fused GSL launch (PROFILE_GSL_ARGS entry) with the same inputs and output buffers."""
     adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out = rec
-    G, N, H = feat.shape
-    _lib.check(_lib.load().get_gsl_fused_f32(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k,
-                                             drop_p, s1, s2, _ptr(score), keep.data_ptr(), out.data_ptr(), _stream()),
-               "get_gsl_fused_f32")
-    return G
+    _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out)
+    return feat.shape[0]
 
 
 def gsl_mask_adj(adj, score, k):
@@ -408,8 +411,165 @@ def _rows2d(t: torch.Tensor) -> torch.Tensor:
 # =================================================================================================
 # GGNN layer (reference Models/BiDAF/wrapper.py:174-208; backward per SURVEY.md Appendix A.1)
 # =================================================================================================
+def _grad_target(param: torch.Tensor, shape=None):
+    """(destination tensor, accumulate?, returned gradient) for a weight / bias gradient: the registered sink view
+    (accumulated in place, nothing returned to autograd) or a fresh tensor."""
+    sink = GRAD_SINK.get(param.data_ptr())
+    if sink is not None:
+        return sink, True, None
+    t = torch.empty(tuple(param.shape) if shape is None else shape, dtype=torch.float32, device=param.device)
+    return t, False, t
+
+
+def _ggnn_packs(H, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, gs):
+    """Packed B operands of one GGNN layer. Activation buffers keep [x | a | r*x] side by side (column blocks of Hp =
+    round_up(H, 8)), the gate-gradient buffer [dz' | dr' | dh'], so every contraction is ONE segment:
+      zr : rows [z: 0..H) [r: gs..gs+H), cols [x: Wz1|Wr1][a: Wz0|Wr0]        A = [x | a]          (K = 2 Hp)
+      h  : rows 0..H, cols [a: Wh0][r*x: Wh1]                                  A = [a | r*x]        (K = 2 Hp)
+      da : rows 0..H, cols [dz': Wz0^T][dr': Wr0^T][dh': Wh0^T]                A = [dz'|dr'|dh']    (K = 3 Hp)
+      dx : rows 0..H, cols [dz': Wz1^T][dr': Wr1^T]                            A = [dz'|dr']        (K = 2 Hp)
+      drx: Wh1^T; p: Wp; pT: Wp^T."""
+    Hp = round_up(H, 8)
+    key = ("ggnn", gs) + tuple(planes._view_key(w) for w in (Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1))
+
+    def b_zr():
+        return 2 * gs, 2 * Hp, [(Wz1, 0, 0), (Wz0, 0, Hp), (Wr1, gs, 0), (Wr0, gs, Hp)], 2 * gs, [(bz0, bz1, 0), (br0, br1, gs)]
+
+    def b_h():
+        return H, 2 * Hp, [(Wh0, 0, 0), (Wh1, 0, Hp)], Hp, [(bh0, bh1, 0)]
+
+    def b_da():
+        return H, 3 * Hp, [(Wz0.t(), 0, 0), (Wr0.t(), 0, Hp), (Wh0.t(), 0, 2 * Hp)], 0, []
+
+    def b_dx():
+        return H, 2 * Hp, [(Wz1.t(), 0, 0), (Wr1.t(), 0, Hp)], 0, []
+    return {"zr": lambda: get_pack(key + ("zr",), b_zr), "h": lambda: get_pack(key + ("h",), b_h),
+            "da": lambda: get_pack(key + ("da",), b_da), "dx": lambda: get_pack(key + ("dx",), b_dx),
+            "drx": lambda: pack_of(Wh1.t()), "p": lambda: pack_of(Wp), "pT": lambda: pack_of(Wp.t())}
+
+
 class GGNNLayerFn(torch.autograd.Function):
     """out = GGNN(adj', x_in).  x_in is either `feat` (G,N,Din) or rows `ids` (G,N) of the frozen `table`.
+    keep (G,N) uint8 restricts the adjacency to edges with a kept endpoint (GSL); pre_agg (bf16 planes tensor of
+    adj' @ drop(x_in), from the fused GSL kernel) replaces the aggregation of the projected features by linearity.
+    Returns (out (G,N,H) fp32, out planes (P, G*N, Hp) bf16 or an empty tensor): the planes feed the next contraction."""
+
+    @staticmethod
+    def forward(ctx, adj, feat, table, ids, keep, pre_agg, p_drop, seed,
+                Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, exact_fwd=False, out_planes=0):
+        G, N = adj.shape[0], adj.shape[1]
+        M = G * N
+        H, Din = Wp.shape
+        Hp = round_up(H, 8)
+        dev = adj.device
+        adj = adj.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        mode = gemm_mode(exact_fwd)
+        bn = planes.tile_n(M, H, mode)
+        gs = round_up(Hp, bn)
+        pk = _ggnn_packs(H, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, gs)
+        # projection input (embedding gather and / or dropout) written ONCE as planes: read by the forward projection and
+        # by the weight gradient dWp
+        if feat is not None:
+            xd = rows_gather_dropout_planes(_rows2d(feat), None, M, p_drop, seed, mode)
+        else:
+            _chk_f32(table, "table")
+            xd = rows_gather_dropout_planes(table, ids.reshape(-1).to(torch.int64).contiguous(), M, p_drop, seed, mode)
+        xar = alloc_planes(mode, M, 3 * Hp, dev)          # [x | a | r*x]
+        xP, aP, rxP = xar.view_cols(0, H), xar.view_cols(Hp, H), xar.view_cols(2 * Hp, H)
+        x = torch.empty((M, H), **f32)
+        gemm_bp([(xd, pk["p"]().planes, Din)], M, H, mode=mode, C=x, planes_out=xP)
+        if pre_agg is not None:
+            gemm_bp([(Planes(pre_agg, Din), pk["p"]().planes, Din)], M, H, mode=mode, planes_out=aP, pad_one=True)
+        else:
+            graph_aggregate(adj, x.view(G, N, H), keep, planes_out=aP, pad_one=True, want_f32=False)
+        z = torch.empty((M, H), **f32)
+        r = torch.empty((M, H), **f32)
+        h = torch.empty((M, H), **f32)
+        out = torch.empty((M, H), **f32)
+        pzr = pk["zr"]()
+        gemm_bp([(xar.view_cols(0, 2 * Hp), pzr.planes, 2 * Hp)], M, 2 * gs, mode=mode, epilogue=BPE_ZR, C=z, out1=r,
+                bias=pzr.bias, aux0=x, planes_out=rxP, zr=(gs, H), tn=bn)
+        ph = pk["h"]()
+        op = alloc_planes(out_planes, M, H, dev) if out_planes else None
+        gemm_bp([(xar.view_cols(Hp, 2 * Hp), ph.planes, 2 * Hp)], M, H, mode=mode, epilogue=BPE_TANH_BLEND, C=out, out1=h,
+                bias=ph.bias, aux0=z, aux1=x, planes_out=op)
+        ctx.save_for_backward(adj, keep, xd.t, xar.t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1)
+        ctx.p_drop, ctx.seed, ctx.dims, ctx.has_feat, ctx.gs = p_drop, seed, (G, N, H, Din), feat is not None, gs
+        op_t = op.t if op is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)
+        ctx.mark_non_differentiable(op_t)
+        return out.view(G, N, H), op_t
+
+    @staticmethod
+    def backward(ctx, dout, _dplanes):
+        (adj, keep, xd_t, xar_t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1) = ctx.saved_tensors
+        G, N, H, Din = ctx.dims
+        M = G * N
+        Hp = round_up(H, 8)
+        dev = dout.device
+        lib = _lib.load()
+        mode = gemm_mode(False)
+        pk = _ggnn_packs(H, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, ctx.gs)
+        xd, xar = Planes(xd_t, Din), Planes(xar_t, 3 * Hp)
+        dout = dout.contiguous().view(M, H)
+        # gate gradients as planes, side by side [dz' | dr' | dh']: the contractions below and the weight gradients that
+        # share an activation operand are ONE tensor-core launch each
+        dg = alloc_planes(mode, M, 3 * Hp, dev)
+        dx = torch.empty((M, H), dtype=torch.float32, device=dev)
+        _lib.check(lib.get_ggnn_gate_bwd_bp(dout.data_ptr(), z.data_ptr(), h.data_ptr(), x.data_ptr(), M, H, dg.ptr, dg.ld,
+                                            dg.plane_stride, mode, 0, 2 * Hp, dx.data_ptr(), _stream()), "get_ggnn_gate_bwd_bp")
+        # d(rx) = dh' @ Wh1 ; dr' = d(rx)*x*r*(1-r) -> planes ; dx += d(rx)*r
+        gemm_bp([(dg.view_cols(2 * Hp, H), pk["drx"]().planes, H)], M, H, mode=mode, epilogue=BPE_DGATE_R, aux0=x, aux1=r,
+                out1=dx, planes_out=dg.view_cols(Hp, H))
+        # da = dz'@Wz0 + dr'@Wr0 + dh'@Wh0
+        da = torch.empty((M, H), dtype=torch.float32, device=dev)
+        gemm_bp([(dg.view_cols(0, 3 * Hp), pk["da"]().planes, 3 * Hp)], M, H, mode=mode, C=da)
+        # dx += dz'@Wz1 + dr'@Wr1 + adj'^T @ da ; the aggregation kernel also writes the planes of the final dx
+        gemm_bp([(dg.view_cols(0, 2 * Hp), pk["dx"]().planes, 2 * Hp)], M, H, mode=mode, C=dx, accumulate=True)
+        dxP = alloc_planes(mode, M, H, dev)
+        graph_aggregate(adj, da.view(G, N, H), keep, out=dx.view(G, N, H), transpose=True, accumulate=True, planes_out=dxP)
+        need = ctx.needs_input_grad
+        grads = [None] * 23
+        # order of inputs: ... 8:Wp 9:Wz0 10:bz0 11:Wz1 12:bz1 13:Wr0 14:br0 15:Wr1 16:br1 17:Wh0 18:bh0 19:Wh1 20:bh1
+        xP, aP1, rxP = xar.view_cols(0, H), xar.view_cols(Hp, Hp), xar.view_cols(2 * Hp, H)
+        if need[9] or need[13] or need[17] or need[10] or need[14] or need[18]:
+            # [dWz0; dWr0; dWh0 | db] = [dz'|dr'|dh']^T [a | 1]: the ones column of the `a` block yields the bias gradients
+            dsts = []
+            for i_w, i_b0, i_b1, r0, W, b0, b1 in ((9, 10, 12, 0, Wz0, bz0, bz1), (13, 14, 16, Hp, Wr0, br0, br1),
+                                                   (17, 18, 20, 2 * Hp, Wh0, bh0, bh1)):
+                t, acc, g = _grad_target(W)
+                assert acc == bool(GRAD_SINK), "grad sinks must cover all GGNN parameters or none"
+                dsts.append((t, r0, H, 0, H)); grads[i_w] = g
+                for i_b, bb in ((i_b0, b0), (i_b1, b1)):
+                    t, _, g = _grad_target(bb)
+                    dsts.append((t, r0, H, H, 1)); grads[i_b] = g
+            wgrad_bp(dg.view_cols(0, 3 * Hp).T(), aP1.T(), 3 * Hp, Hp, M, mode, dsts, accumulate=bool(GRAD_SINK))
+        if need[11] or need[15]:
+            dsts = []
+            for i_w, r0, W in ((11, 0, Wz1), (15, Hp, Wr1)):
+                t, acc, g = _grad_target(W)
+                dsts.append((t, r0, H, 0, H)); grads[i_w] = g
+            wgrad_bp(dg.view_cols(0, 2 * Hp).T(), xP.T(), 2 * Hp, H, M, mode, dsts, accumulate=bool(GRAD_SINK))
+        if need[19]:
+            t, acc, g = _grad_target(Wh1)
+            grads[19] = g
+            wgrad_bp(dg.view_cols(2 * Hp, H).T(), rxP.T(), H, H, M, mode, [(t, 0, H, 0, H)], accumulate=acc)
+        if need[8]:
+            t, acc, g = _grad_target(Wp)
+            grads[8] = g
+            wgrad_bp(dxP.T(), xd.T(), H, Din, M, mode, [(t, 0, H, 0, Din)], accumulate=acc)
+        if ctx.has_feat and need[1]:
+            dfeat = torch.empty((M, Din), dtype=torch.float32, device=dev)
+            gemm_bp([(dxP, pk["pT"]().planes, H)], M, Din, mode=mode, C=dfeat,
+                    drop_out=(ctx.p_drop, ctx.seed) if ctx.p_drop > 0 else None)
+            grads[1] = dfeat.view(G, N, Din)
+        return tuple(grads)
+
+
+class GGNNLayerSimtFn(torch.autograd.Function):
+    """Exact-fp32 SIMT implementation for small / odd shapes (M < 128 rows, feature sizes not multiples of 4, e.g. the
+    stand-alone GGNN(H -> 1) surface): the same computation as GGNNLayerFn without tensor cores.
+    out = GGNN(adj', x_in).  x_in is either `feat` (G,N,Din) or rows `ids` (G,N) of the frozen `table`.
     keep (G,N) uint8 restricts the adjacency to edges with a kept endpoint (GSL); pre_agg = adj' @ drop(x_in)
     (from the fused GSL kernel) replaces the aggregation of the projected features by linearity."""
 
@@ -432,10 +592,10 @@ class GGNNLayerFn(torch.autograd.Function):
             _chk_f32(table, "table")
             rowidx = ids.reshape(-1).to(torch.int64).contiguous()
             xd = rows_gather_dropout(table, rowidx, M, p_drop, seed)
-        gemm([(xd, Wp)], x, tc=True, exact=exact_fwd)
+        gemm([(xd, Wp)], x)
         a = torch.empty((M, H), **f32)
         if pre_agg is not None:
-            gemm([(_rows2d(pre_agg), Wp)], a, tc=True, exact=exact_fwd)
+            gemm([(_rows2d(pre_agg), Wp)], a)
         else:
             graph_aggregate(adj, x.view(G, N, H), keep, out=a.view(G, N, H))
         z = torch.empty((M, H), **f32)
@@ -443,10 +603,9 @@ class GGNNLayerFn(torch.autograd.Function):
         rx = torch.empty((M, H), **f32)
         h = torch.empty((M, H), **f32)
         out = torch.empty((M, H), **f32)
-        gemm([(a, Wz0), (x, Wz1)], z, epilogue=EPI_SIGMOID, bias0=bz0, bias1=bz1, tc=True, exact=exact_fwd)
-        gemm([(a, Wr0), (x, Wr1)], r, epilogue=EPI_SIGMOID, bias0=br0, bias1=br1, aux0=x, out1=rx, tc=True, exact=exact_fwd)
-        gemm([(a, Wh0), (rx, Wh1)], out, epilogue=EPI_TANH_BLEND, bias0=bh0, bias1=bh1, aux0=z, aux1=x, out1=h,
-             tc=True, exact=exact_fwd)
+        gemm([(a, Wz0), (x, Wz1)], z, epilogue=EPI_SIGMOID, bias0=bz0, bias1=bz1)
+        gemm([(a, Wr0), (x, Wr1)], r, epilogue=EPI_SIGMOID, bias0=br0, bias1=br1, aux0=x, out1=rx)
+        gemm([(a, Wh0), (rx, Wh1)], out, epilogue=EPI_TANH_BLEND, bias0=bh0, bias1=bh1, aux0=z, aux1=x, out1=h)
         ctx.save_for_backward(adj, xd, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1)
         ctx.p_drop, ctx.seed, ctx.dims, ctx.has_feat = p_drop, seed, (G, N, H, Din), feat is not None
         return out.view(G, N, H)
@@ -470,26 +629,26 @@ class GGNNLayerFn(torch.autograd.Function):
                                              dhp.data_ptr(), dzp.data_ptr(), dx.data_ptr(), _stream()),
                    "get_ggnn_gate_bwd_f32")
         # d(rx) = dhp @ Wh1 ; drp = d(rx)*x*r*(1-r) ; dx += d(rx)*r
-        gemm([(dhp, Wh1.t())], drp, epilogue=EPI_DGATE_R, aux0=x, aux1=r, out1=dx, tc=True)
+        gemm([(dhp, Wh1.t())], drp, epilogue=EPI_DGATE_R, aux0=x, aux1=r, out1=dx)
         # da = dhp@Wh0 + dzp@Wz0 + drp@Wr0
-        gemm([(dhp, Wh0.t()), (dzp, Wz0.t()), (drp, Wr0.t())], da, tc=True)
+        gemm([(dhp, Wh0.t()), (dzp, Wz0.t()), (drp, Wr0.t())], da)
         # dx += dzp@Wz1 + drp@Wr1 + adj'^T @ da
-        gemm([(dzp, Wz1.t()), (drp, Wr1.t())], dx, accumulate=True, tc=True)
+        gemm([(dzp, Wz1.t()), (drp, Wr1.t())], dx, accumulate=True)
         graph_aggregate(adj, da.view(G, N, H), keep, out=dx.view(G, N, H), transpose=True, accumulate=True)
         need = ctx.needs_input_grad
         grads = [None] * 22
         # order of inputs: ... 8:Wp 9:Wz0 10:bz0 11:Wz1 12:bz1 13:Wr0 14:br0 15:Wr1 16:br1 17:Wh0 18:bh0 19:Wh1 20:bh1
         if need[9] or need[13] or need[17]:
             wa = torch.empty((3 * H, H), **f32)                      # [dWz0; dWr0; dWh0]
-            gemm([(dg.t(), a.t())], wa, tc=True, presplit=False)
+            gemm([(dg.t(), a.t())], wa)
             grads[9], grads[13], grads[17] = wa[:H], wa[H:2 * H], wa[2 * H:]
         if need[11] or need[15]:
             wx = torch.empty((2 * H, H), **f32)                      # [dWz1; dWr1]
-            gemm([(dg[:, :2 * H].t(), x.t())], wx, tc=True, presplit=False)
+            gemm([(dg[:, :2 * H].t(), x.t())], wx)
             grads[11], grads[15] = wx[:H], wx[H:]
         if need[19]:
             w = torch.empty((H, H), **f32)
-            gemm([(dhp.t(), rx.t())], w, tc=True, presplit=False)
+            gemm([(dhp.t(), rx.t())], w)
             grads[19] = w
         if any(need[i] for i in (10, 12, 14, 16, 18, 20)):
             gb = colsum(dg)                                          # [dbz | dbr | dbh]
@@ -499,22 +658,36 @@ class GGNNLayerFn(torch.autograd.Function):
         if need[8]:
             # dWp^T (Din,H) = Xd^T @ dx on the materialised projection input
             wT = torch.empty((Din, H), **f32)
-            gemm([(xd.t(), dx.t())], wT, tc=True, presplit=False)
+            gemm([(xd.t(), dx.t())], wT)
             grads[8] = wT.t()
         if ctx.has_feat and need[1]:
             dfeat = torch.empty((M, Din), **f32)
             if ctx.p_drop > 0:
-                gemm([(dx, Wp.t())], dfeat, epilogue=EPI_DROPOUT_OUT, drop_out_p=ctx.p_drop, drop_out_seed=ctx.seed,
-                     tc=True)
+                gemm([(dx, Wp.t())], dfeat, epilogue=EPI_DROPOUT_OUT, drop_out_p=ctx.p_drop, drop_out_seed=ctx.seed)
             else:
-                gemm([(dx, Wp.t())], dfeat, tc=True)
+                gemm([(dx, Wp.t())], dfeat)
             grads[1] = dfeat.view(G, N, Din)
         return tuple(grads)
 
 
-def ggnn_layer(adj, feat, table, ids, keep, pre_agg, p_drop, seed, params: Sequence[torch.Tensor], exact_fwd: bool = False):
-    """exact_fwd=True: the forward contractions stay fp32-accurate in every precision mode (feat_prop1: GSL top-k chain)."""
-    return GGNNLayerFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params, bool(exact_fwd))
+def layer_uses_tc(M: int, H: int, Din: int) -> bool:
+    """Does a GGNN layer of these sizes run on the tensor-core plane path (else: exact SIMT path)?"""
+    return bool(TC_ENABLED and M >= 128 and H % 4 == 0 and Din % 4 == 0 and H >= 8 and Din >= 8)
+
+
+def ggnn_layer(adj, feat, table, ids, keep, pre_agg, p_drop, seed, params: Sequence[torch.Tensor], exact_fwd: bool = False,
+               out_planes: int = 0):
+    """exact_fwd=True: the forward contractions stay fp32-exact in every precision mode (feat_prop1: GSL top-k chain).
+    Returns (out, planes tensor of out | None). Large regular shapes run on the tensor cores; the rest on the SIMT path."""
+    H, Din = params[0].shape
+    M = adj.shape[0] * adj.shape[1]
+    if layer_uses_tc(M, H, Din):
+        out, op = GGNNLayerFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params, bool(exact_fwd),
+                                    int(out_planes))
+        return out, (op if out_planes else None)
+    if isinstance(pre_agg, torch.Tensor) and pre_agg.dtype == torch.bfloat16:
+        pre_agg = Planes(pre_agg, Din).to_float().view(adj.shape[0], adj.shape[1], Din)
+    return GGNNLayerSimtFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params, bool(exact_fwd)), None
 
 
 # =================================================================================================
@@ -522,8 +695,10 @@ def ggnn_layer(adj, feat, table, ids, keep, pre_agg, p_drop, seed, params: Seque
 # (reference thirdparty/two_branches_attention.py:121-148, thirdparty/self_attention.py:75-100)
 # =================================================================================================
 class ConcatAttFn(torch.autograd.Function):
+    """right_planes: optional bf16 plane tensor of `right` (written by the producing GEMM's epilogue)."""
+
     @staticmethod
-    def forward(ctx, left, right, mask_u8, W1, W2):
+    def forward(ctx, left, right, mask_u8, W1, W2, right_planes=None):
         lib = _lib.load()
         G, P, Dr = right.shape
         H = W1.shape[0]
@@ -534,27 +709,30 @@ class ConcatAttFn(torch.autograd.Function):
         right2d = _rows2d(right)
         W1 = W1.contiguous()
         W2 = W2.contiguous()
+        rP = Planes(right_planes, Dr) if right_planes is not None else None
+        if rP is None and TC_ENABLED and G * P >= 128 and Dr % 4 == 0 and H % 4 == 0:
+            rP = to_planes(right2d, gemm_mode(False))          # converted once: forward projection + weight gradient
         t = torch.empty((G * P, H), **f32)
         if left is not None:
             lp = torch.empty((G, H), **f32)
             gemm([(left.contiguous(), W1[:, :X])], lp, tc=True)
-            gemm([(right2d, W1[:, X:])], t, epilogue=EPI_TANH_ROWGROUP, aux0=lp, group_rows=P, tc=True)
+            gemm([(rP if rP is not None else right2d, W1[:, X:])], t, epilogue=EPI_TANH_ROWGROUP, aux0=lp, group_rows=P, tc=True)
         else:
-            gemm([(right2d, W1)], t, epilogue=EPI_TANH, tc=True)
+            gemm([(rP if rP is not None else right2d, W1)], t, epilogue=EPI_TANH, tc=True)
         att = torch.empty((G, P, Cn), **f32)
         pooled = torch.empty((G, Dr, Cn), **f32)
         mask_u8 = mask_u8.contiguous()
         _lib.check(lib.get_att_pool_fwd_f32(t.data_ptr(), right2d.data_ptr(), _ld(right2d), W2.data_ptr(),
                                             mask_u8.data_ptr(), G, P, H, Dr, Cn, att.data_ptr(), pooled.data_ptr(),
                                             Dr * Cn, _stream()), "get_att_pool_fwd_f32")
-        ctx.save_for_backward(left, right2d, W1, W2, t, att)
+        ctx.save_for_backward(left, right2d, W1, W2, t, att, rP.t if rP is not None else None)
         ctx.dims = (G, P, H, Dr, Cn, X)
         return pooled, att
 
     @staticmethod
     def backward(ctx, d_pooled, d_att):
         lib = _lib.load()
-        left, right2d, W1, W2, t, att = ctx.saved_tensors
+        left, right2d, W1, W2, t, att, rP_t = ctx.saved_tensors
         G, P, H, Dr, Cn, X = ctx.dims
         dev = right2d.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -574,25 +752,36 @@ class ConcatAttFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         dleft = dW1 = dW2 = None
         W1R = W1[:, X:]
+        use_tc = rP_t is not None
+        duP = to_planes(du, gemm_mode(False)) if use_tc and (need[1] or need[3]) else None
         if need[1]:
-            gemm([(du, W1R.t())], dright, accumulate=True, tc=True)
+            gemm([(duP if duP is not None else du, W1R.t())], dright, accumulate=True, tc=True)
         if need[4]:
             dW2 = torch.empty((Cn, H), **f32)
             gemm([(de.t(), t.t())], dW2)
         if need[3]:
-            dW1 = torch.empty((H, X + Dr), **f32)
-            gemm([(du.t(), right2d.t())], dW1[:, X:], tc=True, presplit=False)
+            sink = GRAD_SINK.get(W1.data_ptr())
+            dW1 = sink if sink is not None else torch.empty((H, X + Dr), **f32)
+            if sink is None and left is None:
+                pass
+            if use_tc:
+                gemm([(duP, Planes(rP_t, Dr))], dW1[:, X:], tc=True, presplit=False, accumulate=sink is not None)
+            else:
+                assert sink is None
+                gemm([(du.t(), right2d.t())], dW1[:, X:])
             if left is not None:
-                gemm([(du_sum.t(), left.contiguous().t())], dW1[:, :X])
+                gemm([(du_sum.t(), left.contiguous().t())], dW1[:, :X], accumulate=sink is not None)
+            if sink is not None:
+                dW1 = None
         if left is not None and need[0]:
             dleft = torch.empty((G, X), **f32)
             gemm([(du_sum, W1[:, :X].t())], dleft, tc=True)
-        return dleft, (dright.view(G, P, Dr) if need[1] else None), None, dW1, dW2
+        return dleft, (dright.view(G, P, Dr) if need[1] else None), None, dW1, dW2, None
 
 
-def concat_att(left, right, mask, W1, W2):
+def concat_att(left, right, mask, W1, W2, right_planes=None):
     mask_u8 = (mask != 0).to(torch.uint8)
-    return ConcatAttFn.apply(left, right, mask_u8, W1, W2)
+    return ConcatAttFn.apply(left, right, mask_u8, W1, W2, right_planes)
 
 
 # =================================================================================================

@@ -27,10 +27,12 @@
 extern "C" {
 #endif
 
-#define GET_B200_ABI_VERSION 1
+#define GET_B200_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------------------
- * Dense contraction with fused epilogues (the `Linear`s of GGNN / attention / output MLP).
+ * Dense contraction with fused epilogues, exact fp32 on the CUDA cores: the small / odd `Linear`s (output MLP, per-claim
+ * projections, head-mix weight gradients, op-level surfaces with sizes the tensor-core path does not take). The large
+ * contractions of GGNN / attention run through get_gemm_bp below.
  * Replaces: wrapper.py:191,194-204 (seven nn.Linear per GGNN), tba.py:140-141, sa.py:89-90,
  *           gbss.py:121 (output MLP), gbss.py:100,150 (embedding gather fused into the A operand),
  *           wrapper.py:189-190 (nn.Dropout fused into the A operand), and their autograd backward.
@@ -90,52 +92,118 @@ typedef struct get_gemm_desc {
    * order by a second kernel (deterministic), then the epilogue is applied. */
   int32_t split_k; int32_t _pad1;
   float* workspace;
-  /* Tensor-core path (tcgen05, 3xTF32 error-compensated: fp32-level accuracy), offered when tc_mode == 1; the library
-   * takes it when the descriptor is eligible and otherwise falls back to the exact SIMT path:
-   *  (a) persistent TMA-fed kernel: every A segment 16-byte aligned with ld % 4 == 0, no row gather, no A dropout, all
-   *      segments with the same `trans`; B either given pre-split (below) or raw with the same `trans` in all segments.
-   *      Operands with trans == 1 (both activations: weight gradients) are consumed MN-major, no transposition pass.
-   *      split_k > 1 is honoured (k blocks of 32) through `workspace`.
-   *  (b) register-staged kernel for gathered / dropped-out A operands: A contiguous along k (trans == 0, ld % 4 == 0,
-   *      K % 4 == 0, K >= 32), no split-K, B pre-split.
-   * Pre-split B: two k-contiguous (N, K[s]) row-major matrices B_hi[s] (tf32-rounded) and B_lo[s] (= B - B_hi) with
-   * leading dimension ld_split[s] (see get_split_tf32_f32; a transposed B is simply split into a k-contiguous copy).
-   * B[s] stays the original operand for the fallback. tc_n_tiles: CTA tiles along N (0 = auto).
-   * tc_mode == 2: reduced-precision mode of kernel (a): ONE tf32 pass on the raw operands (no hi/lo split, B_lo unused),
-   * relative error ~1e-3 -- for the 1e-2 parity class (BASELINE.json configs[2]) and never for the layer that feeds the
-   * GSL top-k. */
-  const float* B_hi[GET_GEMM_MAX_SEG];
-  const float* B_lo[GET_GEMM_MAX_SEG];
-  int64_t ld_split[GET_GEMM_MAX_SEG];
-  int32_t tc_mode; int32_t tc_n_tiles;
 } get_gemm_desc;
 
 int get_gemm_f32(const get_gemm_desc* desc, void* stream);
 
-/* 2 / 1 if the descriptor would run on the tcgen05 path (persistent TMA-fed / register-staged kernel), 0 if on the
- * SIMT path, <0 on invalid descriptors. */
-int get_gemm_f32_uses_tc(const get_gemm_desc* desc);
-
-/* Error-compensated TF32 split of a weight matrix for the tensor-core path:
- * hi = tf32_round_nearest(src), lo = tf32_round_nearest(src - hi). src is a logical (rows, cols) matrix addressed as
- * src[r*ld_r + c*ld_c] (so a transposed view can be split into a k-contiguous copy); hi/lo are (rows, cols)
- * row-major with leading dimension ld_out. */
-int get_split_tf32_f32(const float* src, int64_t ld_r, int64_t ld_c, int rows, int cols,
-                       float* hi, float* lo, int64_t ld_out, void* stream);
-
-/* The same split for MANY matrices in one launch (all weights of the model once per optimizer step). `jobs` is an array
- * in DEVICE memory; job j covers blocks [first_block, first_block + ceil(rows*cols/256)) of the launch, first_block
- * ascending from 0; total_blocks = sum over jobs. */
-typedef struct get_split_job {
-  const float* src; int64_t ld_r, ld_c;
-  int32_t rows, cols;
-  float* hi; float* lo; int64_t ld_out;
-  int64_t first_block;
-} get_split_job;
-int get_split_tf32_multi_f32(const get_split_job* jobs, int n_jobs, int64_t total_blocks, void* stream);
-
 /* Number of kernels get_gemm_f32 will launch for this descriptor (1, or 2 with split-K). */
 int get_gemm_f32_launches(const get_gemm_desc* desc);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core contraction on bf16 PLANES (tcgen05.mma.kind::f16, TMA-fed, persistent) -- the main path of every large
+ * `Linear` of GGNN / attention and of their backward passes (same reference call sites as get_gemm_f32).
+ *
+ * A fp32 value v is carried as up to three bf16 planes p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1).
+ * A plane tensor is bf16 [planes][rows][ld] (ld % 8 == 0, plane_stride % 8 == 0, 16-byte aligned); columns between
+ * the logical width and ld are padding the PRODUCER writes (zeros, or 1.0 in the first pad column when `pad_one`).
+ * Planes are produced by the kernels that produce the activation (GEMM epilogues, graph kernels, element-wise
+ * kernels) or by get_to_planes_bf16; weights are packed once per optimizer step by get_pack_planes_multi.
+ *
+ *   acc[m,n] = sum_s sum_{k<K[s]} A_s(m,k) * B_s(n,k)      with the plane products selected by `mode`:
+ *     mode 1:  a0.b0                                        (plain bf16: the 1e-2 parity class, BASELINE configs[2])
+ *     mode 2:  a0.b0 + a0.b1 + a1.b0                        (16-bit operands: relative error ~1e-5, fp32 parity class)
+ *     mode 3:  a0.b0  |  a0.b1 + a1.b0 + a1.b1 + a0.b2 + a2.b0   (fp32-exact class; the small terms accumulate in
+ *              their own TMEM accumulator and are added in the epilogue: the layer that feeds the GSL top-k)
+ *   operand (trans == 0, "K-major"):  op(i,k) = plane[i*ld + k]      (activations as A, packed weights as B)
+ *   operand (trans == 1, "MN-major"): op(i,k) = plane[k*ld + i]      (both operands of a weight gradient dW = dG^T X)
+ * All segments share `trans` per side. split_k > 1: raw partial tiles go to `workspace` ([split][M][ws_ld] fp32,
+ * ws_ld = get_gemm_bp_ws_ld(desc)) and the caller finishes with get_bp_splitk_reduce (fixed order: deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct get_bp_tensor {
+  const void* ptr;        /* bf16 */
+  int64_t ld;             /* elements per row */
+  int64_t plane_stride;   /* elements between planes */
+  int32_t planes;         /* planes available (>= what `mode` needs) */
+  int32_t trans;
+} get_bp_tensor;
+
+enum get_bp_epilogue {
+  GET_BPE_STORE = 0,        /* v = acc + bias[n] (+ C if accumulate), optional dropout-out mask; C = v; planes_out = v          */
+  GET_BPE_ZR = 1,           /* fused z|r gates (wrapper.py:194-200): s = sigmoid(acc + bias[n]); g = n / zr_group_stride,
+                               c = n % zr_group_stride (< zr_cols): g == 0: C[m,c] = s (z); g == 1: out1[m,c] = s (r),
+                               planes_out[m,c] = s * aux0[m,c] (r*x)                                                          */
+  GET_BPE_TANH_BLEND = 2,   /* h = tanh(acc + bias); out1 = h; C = planes_out = h*aux0 + aux1*(1-aux0) (aux0 = z, aux1 = x)   */
+  GET_BPE_TANH_ROWGROUP = 3,/* C = tanh(acc + aux0[(m / group_rows) * ld_aux0 + n])                                           */
+  GET_BPE_DGATE_R = 4,      /* g = acc; planes_out = g*aux0*aux1*(1-aux1) (aux0 = x, aux1 = r); out1 += g*aux1               */
+  GET_BPE_TANH = 5          /* C = tanh(acc)                                                                                  */
+};
+
+typedef struct get_gemm_bp_desc {
+  get_bp_tensor A[GET_GEMM_MAX_SEG];
+  get_bp_tensor B[GET_GEMM_MAX_SEG];
+  int32_t K[GET_GEMM_MAX_SEG];
+  int32_t nseg;
+  int32_t M, N;
+  int32_t mode;             /* 1, 2 or 3 */
+  int32_t tile_n;           /* CTA tile along N (multiple of 16, <= 256); 0 = library choice (get_gemm_bp_tile_n) */
+  int32_t epilogue;         /* enum get_bp_epilogue */
+  int32_t accumulate;       /* STORE only: C += v */
+  float* C; int64_t ldc;    /* fp32 output or NULL */
+  float* out1; int64_t ld_out1;
+  const float* bias;        /* [N] or NULL */
+  const float* aux0; int64_t ld_aux0;
+  const float* aux1; int64_t ld_aux1;
+  void* planes_out;         /* bf16 plane tensor written by the epilogue, or NULL */
+  int64_t ld_planes_out, planes_out_stride;
+  int32_t planes_out_n;     /* 1..3 */
+  int32_t planes_out_pad_one;
+  int32_t group_rows;       /* TANH_ROWGROUP */
+  int32_t zr_group_stride, zr_cols;   /* ZR */
+  float drop_out_p; uint32_t drop_out_seed;   /* STORE: C = v * keep(seed, m*N + n)/(1-p) when drop_out_p > 0 */
+  int32_t split_k;
+  int32_t kblock;           /* k elements per pipeline stage: 32 or 64; 0 = library choice */
+  float* workspace; int64_t workspace_floats;
+} get_gemm_bp_desc;
+
+/* 0 = launched; negative = invalid / unsupported descriptor (the Python host then raises: there is no silent fallback) */
+int get_gemm_bp(const get_gemm_bp_desc* desc, void* stream);
+/* N tile the library picks for (M, N, mode) (what zr_group_stride must be a multiple of); row pitch of the split-K
+ * workspace; number of k splits the launch will really use. */
+int get_gemm_bp_tile_n(int M, int N, int mode);
+int64_t get_gemm_bp_ws_ld(const get_gemm_bp_desc* desc);
+int get_gemm_bp_splits(const get_gemm_bp_desc* desc);
+
+/* Fixed-order reduction of split-K partial tiles into up to GET_BP_MAX_DST destination blocks (the weight / bias
+ * gradients, written straight into the flat gradient bucket): for every block b and (r, c) inside it
+ *   dst_b[(r - row0) * ld + (c - col0)] = (accumulate ? dst_b[..] : 0) + sum_z ws[(z*M + r)*ws_ld + c]. */
+#define GET_BP_MAX_DST 12
+typedef struct get_bp_dst {
+  float* dst; int64_t ld;
+  int32_t row0, nrows, col0, ncols;
+} get_bp_dst;
+int get_bp_splitk_reduce(const float* workspace, int splits, int M, int64_t ws_ld, const get_bp_dst* dsts, int ndst,
+                         int accumulate, void* stream);
+
+/* fp32 (rows, cols) matrix with row stride ld_src -> bf16 planes [nplanes][rows][ld_out]; the pad columns from `cols`
+ * up to the next multiple of 8 (at most ld_out) are written too (zeros; 1.0 at column `cols` when pad_one). */
+int get_to_planes_bf16(const float* src, int64_t ld_src, int rows, int cols, void* planes, int64_t ld_out,
+                       int64_t plane_stride, int nplanes, int pad_one, void* stream);
+
+/* Weight packing, MANY jobs in one launch (all weights of the model once per optimizer step). `jobs` lives in DEVICE
+ * memory. kind 0: 3 bf16 planes of the logical (rows, cols) matrix src[r*ld_r + c*ld_c] into dst (bf16, row pitch
+ * ld_out, plane pitch plane_stride; dst already points at the block's first element, so several matrices can be packed
+ * side by side / stacked into one plane tensor whose padding was zeroed once). kind 1: fp32 vector
+ * dst[i] = src[i] + (src2 ? src2[i] : 0), i < rows (fused bias vectors). Job j covers blocks
+ * [first_block, first_block + ceil(rows*max(cols,1)/256)) of the launch. */
+typedef struct get_pack_job {
+  const float* src; const float* src2;
+  int64_t ld_r, ld_c;
+  int32_t rows, cols;
+  void* dst; int64_t ld_out, plane_stride;
+  int64_t first_block;
+  int32_t kind, _pad;
+} get_pack_job;
+int get_pack_planes_multi(const get_pack_job* jobs, int n_jobs, int64_t total_blocks, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Neighbour aggregation  out[g] (+)= op(adj'[g]) @ x[g]   with adj'[i,j] = adj[i,j] * (keep[i] | keep[j]).
@@ -160,6 +228,16 @@ int get_gsl_fused_f32(const float* adj, const float* F, const float* wp, const f
                       int G, int N, int H, int k,
                       float drop_p, uint32_t seed_scorer, uint32_t seed_layer2,
                       float* score, uint8_t* keep, float* out, void* stream);
+
+/* The two graph kernels with the output rows written as bf16 planes [nplanes][G*N][ld_p] for the next tensor-core
+ * contraction (see get_gemm_bp; pad columns H..round_up(H,8)-1 written as zeros, 1.0 in column H when pad_one) and / or
+ * as fp32 (`out` may be NULL when planes are given; accumulate needs `out`). */
+int get_graph_aggregate_bp(const float* adj, const float* x, const uint8_t* keep, float* out, void* planes,
+                           int64_t ld_p, int64_t plane_stride, int nplanes, int pad_one, int G, int N, int H,
+                           int transpose, int accumulate, void* stream);
+int get_gsl_fused_bp(const float* adj, const float* F, const float* wp, const float* gate, int G, int N, int H, int k,
+                     float drop_p, uint32_t seed_scorer, uint32_t seed_layer2, float* score, uint8_t* keep,
+                     float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
 
 /* GSL.forward as a stand-alone op (wrapper.py:215-227): adj_out = adj * mask(top-k(score)). score (G,N). */
 int get_gsl_mask_adj_f32(const float* adj, const float* score, int G, int N, int k,
@@ -226,6 +304,16 @@ int get_masked_mean_bwd_f32(const float* dout, const int64_t* ids, const int64_t
  * Forward projection and weight gradient then read the same (R, W) matrix through plain TMA tiles. */
 int get_rows_gather_dropout_f32(const float* src, int64_t ld_src, const int64_t* idx, int R, int W, float p,
                                 uint32_t seed, float* out, int64_t ld_out, void* stream);
+
+/* Plane-emitting variants for the bf16-plane contraction (get_gemm_bp): the same computations with the result written
+ * as bf16 planes [nplanes][rows][ld] (pad columns up to the next multiple of 8 written as zeros).
+ * get_ggnn_gate_bwd_bp: dz' -> column block `col_z`, dh' -> column block `col_h` of the gate-gradient plane buffer
+ * [dz' | dr' | dh'] with row pitch ld_g; dx stays fp32 (M,H). */
+int get_ggnn_gate_bwd_bp(const float* dout, const float* z, const float* h, const float* x, int M, int H, void* dg,
+                         int64_t ld_g, int64_t plane_stride, int nplanes, int col_z, int col_h, float* dx, void* stream);
+int get_rows_gather_dropout_bp(const float* src, int64_t ld_src, const int64_t* idx, int R, int W, float p,
+                               uint32_t seed, void* planes, int64_t ld_out, int64_t plane_stride, int nplanes,
+                               void* stream);
 
 /* Dropout salt: one device word per process, added to EVERY dropout seed inside the kernels (effective seed =
  * seed + salt mod 2^32). It is 0 unless set. A captured CUDA graph replays fixed kernel arguments; recording

@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert not missing, "declared in include/get_b200.h but not exported: %s" % missing
     assert sorted(_lib.SIGNATURES.keys()) == declared, "ctypes table and header disagree"
     lib = _lib.load()                      # dlopen + symbol lookup only
-    assert lib.get_b200_abi_version() == 1
+    assert lib.get_b200_abi_version() == 2
     assert lib.get_b200_launch_count() == 0
 
 
@@ -42,8 +42,8 @@ def test_library_is_sm100a_only_and_contains_the_kernels():
     assert archs == {"100a"}, archs
 
 
-def test_gemm_descriptor_layout_matches_header():
-    """sizeof/offsets of the ctypes mirror vs the C struct (compiled with gcc)."""
+def test_descriptor_layouts_match_header():
+    """sizeof/offsets of the ctypes mirrors vs the C structs (compiled with gcc)."""
     import ctypes
     import tempfile
     from get_b200 import _lib
@@ -52,10 +52,15 @@ def test_gemm_descriptor_layout_matches_header():
 #include <stddef.h>
 #include "get_b200.h"
 int main(void){
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(get_gemm_desc), sizeof(get_gemm_operand),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(get_gemm_desc), sizeof(get_gemm_operand),
     offsetof(get_gemm_desc,B), offsetof(get_gemm_desc,K), offsetof(get_gemm_desc,C), offsetof(get_gemm_desc,bias0),
-    offsetof(get_gemm_desc,group_rows), offsetof(get_gemm_desc,drop_out_p), offsetof(get_gemm_desc,workspace),
-    offsetof(get_gemm_desc,ld_split), offsetof(get_gemm_desc,tc_n_tiles));
+    offsetof(get_gemm_desc,group_rows), offsetof(get_gemm_desc,drop_out_p), offsetof(get_gemm_desc,workspace));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(get_gemm_bp_desc), sizeof(get_bp_tensor),
+    offsetof(get_gemm_bp_desc,B), offsetof(get_gemm_bp_desc,K), offsetof(get_gemm_bp_desc,mode), offsetof(get_gemm_bp_desc,C),
+    offsetof(get_gemm_bp_desc,bias), offsetof(get_gemm_bp_desc,planes_out), offsetof(get_gemm_bp_desc,group_rows),
+    offsetof(get_gemm_bp_desc,drop_out_p), offsetof(get_gemm_bp_desc,split_k), offsetof(get_gemm_bp_desc,workspace_floats));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(get_bp_dst), offsetof(get_bp_dst,row0), sizeof(get_pack_job),
+    offsetof(get_pack_job,dst), offsetof(get_pack_job,first_block), offsetof(get_pack_job,kind));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -64,9 +69,12 @@ int main(void){
         exe = os.path.join(d, "t")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         got = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
-    D = _lib.GemmDesc
+    D, B, T, J = _lib.GemmDesc, _lib.GemmBpDesc, _lib.BpDst, _lib.PackJob
     want = [ctypes.sizeof(D), ctypes.sizeof(_lib.GemmOperand), D.B.offset, D.K.offset, D.C.offset, D.bias0.offset,
-            D.group_rows.offset, D.drop_out_p.offset, D.workspace.offset, D.ld_split.offset, D.tc_n_tiles.offset]
+            D.group_rows.offset, D.drop_out_p.offset, D.workspace.offset,
+            ctypes.sizeof(B), ctypes.sizeof(_lib.BpTensor), B.B.offset, B.K.offset, B.mode.offset, B.C.offset, B.bias.offset,
+            B.planes_out.offset, B.group_rows.offset, B.drop_out_p.offset, B.split_k.offset, B.workspace_floats.offset,
+            ctypes.sizeof(T), T.row0.offset, ctypes.sizeof(J), J.dst.offset, J.first_block.offset, J.kind.offset]
     assert got == want
 
 
