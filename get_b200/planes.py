@@ -5,7 +5,7 @@ p2 = bf16(v - p0 - p1)); the tensor-core contraction multiplies planes pairwise 
 class). Activations get their planes from the kernel that produces them; weights are packed once per optimizer step.
 PyTorch is used for device memory only. Nothing here falls back to torch math.
 """
-import ctypes as C
+import ctypes as ct
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -291,7 +291,7 @@ def gemm_bp(segments: Sequence[Tuple[Planes, Planes, int]], M: int, N: int, *, m
     d.split_k, d.kblock = int(split_k), int(kblock)
     if workspace is not None:
         d.workspace, d.workspace_floats = workspace.data_ptr(), workspace.numel()
-    _lib.check(lib.get_gemm_bp(C.byref(d), _stream()), "get_gemm_bp")
+    _lib.check(lib.get_gemm_bp(ct.byref(d), _stream()), "get_gemm_bp")
     return d
 
 
@@ -313,15 +313,15 @@ def wgrad_bp(a: Planes, b: Planes, M: int, N: int, K: int, mode: int, dsts, accu
     d.split_k = min(kblocks, max(2, min(want, max(1, kblocks // 4))))      # >= 2 splits: one code path (partials + reduce)
     d.tile_n = bn
     d.workspace, d.workspace_floats = 16, 1 << 60
-    splits = int(lib.get_gemm_bp_splits(C.byref(d)))
-    ws_ld = int(lib.get_gemm_bp_ws_ld(C.byref(d)))
+    splits = int(lib.get_gemm_bp_splits(ct.byref(d)))
+    ws_ld = int(lib.get_gemm_bp_ws_ld(ct.byref(d)))
     if splits < 1 or ws_ld < 1:
         _lib.check(-1, "get_gemm_bp (planning a weight gradient)")
     ws = torch.empty((splits * M * ws_ld,), dtype=torch.float32, device=a.t.device)
     d.workspace, d.workspace_floats = ws.data_ptr(), ws.numel()
     if splits == 1:       # a contraction of a single k block: plain store in the workspace layout
         d.C, d.ldc = ws.data_ptr(), ws_ld
-    _lib.check(lib.get_gemm_bp(C.byref(d), _stream()), "get_gemm_bp (weight gradient)")
+    _lib.check(lib.get_gemm_bp(ct.byref(d), _stream()), "get_gemm_bp (weight gradient)")
     arr = (_lib.BpDst * len(dsts))()
     for i, (t, r0, nr, c0, nc) in enumerate(dsts):
         assert t.dtype == torch.float32 and t.is_cuda
