@@ -154,10 +154,10 @@ class Graph_basedSemantiStructure(nn.Module):
             blk_seeds = (seeds.get("feat_prop1", 0), seeds.get("word_scorer1", 0), seeds.get("feat_prop2", 0))
         npl = ops.gemm_mode(False)      # planes of the block output: operand of the word-attention projection
         if emb_fused:
-            doc_out, doc_planes = self.ggnn_with_gsl(doc_adj, table=self.embedding.weight, ids=doc, seeds=blk_seeds,
-                                                     out_planes=npl)
+            doc_out = self.ggnn_with_gsl(doc_adj, table=self.embedding.weight, ids=doc, seeds=blk_seeds, out_planes=npl)
         else:
-            doc_out, doc_planes = self.ggnn_with_gsl(doc_adj, self.embedding(doc.long()), seeds=blk_seeds, out_planes=npl)
+            doc_out = self.ggnn_with_gsl(doc_adj, self.embedding(doc.long()), seeds=blk_seeds, out_planes=npl)
+        doc_planes = self.ggnn_with_gsl.last_out_planes
 
         if fork:
             cur.wait_stream(self._side_stream)

@@ -52,6 +52,7 @@ class GGNN(nn.Module):
         self.linearh0 = Linear(out_features, out_features)
         self.linearh1 = Linear(out_features, out_features)
         self.p_drop = float(dropout) if dropout and dropout > 0 else 0.0
+        self.last_out_planes = None   # bf16 planes of the last output when requested (package-internal)
 
     def _params(self):
         return (self.proj.linear.weight,
@@ -66,15 +67,16 @@ class GGNN(nn.Module):
                 out_planes=0):
         """Reference call: forward(adj, x). Extensions used inside this package: (table, ids) = frozen embedding
         table + token ids instead of x (gather fused into the projection), keep / pre_agg from the GSL kernel,
-        explicit dropout seed (tests), out_planes > 0: also return the bf16 planes of the output (the operand of the
-        next tensor-core contraction) -> (out, planes)."""
+        explicit dropout seed (tests), out_planes > 0: also keep the bf16 planes of the output (the operand of the next
+        tensor-core contraction) in `self.last_out_planes`."""
         p = self.p_drop if self.training else 0.0
         if p > 0 and seed is None:
             seed = ops.new_seed()
         adj = adj.float()
         out, op = ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params(), exact_fwd=exact_fwd,
                                  out_planes=out_planes)
-        return (out, op) if out_planes else out
+        self.last_out_planes = op
+        return out
 
 
 class GSL(nn.Module):
@@ -102,6 +104,7 @@ class GGNN_with_GSL(nn.Module):
         self.word_scorer1 = GGNN(hidden_dim, 1, dropout)
         self.gsl1 = GSL(rate)
         self.feat_prop2 = GGNN(hidden_dim, output_dim, dropout)
+        self.last_out_planes = None
         self.last_keep = None     # (G,N) uint8 keep set of the last forward (introspection / tests)
         self.last_score = None
 
@@ -133,7 +136,9 @@ class GGNN_with_GSL(nn.Module):
                                          seed_layer2=seeds[2], want_score=want_score,
                                          planes_n=ops.gemm_mode(False) if tc else 0)
         self.last_keep, self.last_score = keep, score
-        return self.feat_prop2(adj, f1, keep=keep, pre_agg=agg.t if tc else agg, seed=seeds[2], out_planes=out_planes)
+        out = self.feat_prop2(adj, f1, keep=keep, pre_agg=agg.t if tc else agg, seed=seeds[2], out_planes=out_planes)
+        self.last_out_planes = self.feat_prop2.last_out_planes
+        return out
 
 
 class ConcatNotEqualSelfAtt(nn.Module):
