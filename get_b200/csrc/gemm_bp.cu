@@ -35,13 +35,17 @@ constexpr int BP_BM = 128;
 constexpr int BP_THREADS = 320;
 constexpr int BP_EPI_WARPS = 8;
 constexpr int BP_MAX_STAGES = 8;
-constexpr int BP_STG_LD = 36;                          // floats per row of the epilogue staging tile (32 + 4: conflict-free)
-constexpr int BP_STG_BYTES = BP_EPI_WARPS * 32 * BP_STG_LD * 4;
+// epilogue staging: per warp two sets (used alternately: the TMA stores drain asynchronously) of fp32 tiles of 2 KB
+// (C, out1) and bf16 plane tiles of 1 KB; the set size depends on the outputs of the launch (cfg.stg_set, <= 7 KB)
+constexpr int BP_STG_SET_MAX = 7168;
 constexpr int BP_SMS = 148;
 
 struct BpMaps {
   CUtensorMap a[GET_GEMM_MAX_SEG];
   CUtensorMap b[GET_GEMM_MAX_SEG];
+  CUtensorMap c;       // fp32 output (or the split-K workspace), box {16 cols, 32 rows[, 1]}
+  CUtensorMap o1;      // second fp32 output
+  CUtensorMap pl;      // bf16 output planes {cols, rows, planes}, box {16, 32, 1}
 };
 
 struct BpCfg {
@@ -58,166 +62,83 @@ struct BpCfg {
   uint32_t a_lbo, b_lbo, a_sbo, b_sbo, a_kstep, b_kstep, a_lt, b_lt;
   int a_boxes, b_boxes;
   uint32_t a_box_bytes, b_box_bytes;
+  uint32_t stg_set;       // bytes of one epilogue staging set
+  int debug;              // GET_B200_BP_DEBUG=9 with -DGETB_BP_TIMELINE: print the per-role timeline of CTA 0
 };
 
 struct BpParams {
   int M, N, Npad;
   int epilogue, accumulate;
-  float* C; int64_t ldc;
-  float* out1; int64_t ld_out1;
+  const float* C; int64_t ldc;          // read only for accumulate (the stores go through the tensor maps)
+  const float* out1; int64_t ld_out1;   // read only by DGATE_R (dx += ...)
+  int has_c, has_o1, has_pl;
   const float* bias;
   const float* aux0; int64_t ld_aux0;
   const float* aux1; int64_t ld_aux1;
-  __nv_bfloat16* planes; int64_t ld_p, plane_stride;
   int nplanes, pad_one;
   int group_rows, zr_gs, zr_cols, zr_cols_pad;
   uint32_t drop_thr, drop_seed; float drop_scale;
   const uint32_t* salt;
-  float* workspace; int64_t ws_ld;
 };
-
-// ---- fused epilogues on 4 consecutive columns -----------------------------------------------------------------------
-struct BpEpiIn {
-  float a0[4], a1[4], o[4];
-};
-
-__device__ __forceinline__ void bp_ld4(const float* p, float v[4]) {
-  const float4 t = *reinterpret_cast<const float4*>(p);
-  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-__device__ __forceinline__ void bp_st4(float* p, const float v[4]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-
-// classification of a quad starting at tile-global column n: 0 = nothing to do, 1 = real columns, 2 = plane padding only
-template <int EPI>
-__device__ __forceinline__ int bp_quad_kind(const BpParams& p, int n, int& c, int& grp) {
-  if (EPI == GET_BPE_ZR) {
-    grp = n / p.zr_gs;
-    c = n - grp * p.zr_gs;
-    if (grp > 1) return 0;
-    if (c < p.zr_cols) return 1;
-    return (grp == 1 && c < p.zr_cols_pad) ? 2 : 0;
-  }
-  c = n; grp = 0;
-  if (n < p.N) return 1;
-  return (p.planes && n < p.Npad) ? 2 : 0;
-}
-
-template <int EPI>
-__device__ __forceinline__ void bp_epi_load(const BpParams& p, int m, int c, int grp, BpEpiIn& in) {
-  switch (EPI) {
-    case GET_BPE_STORE:
-      if (p.accumulate) bp_ld4(p.C + (int64_t)m * p.ldc + c, in.o);
-      break;
-    case GET_BPE_ZR:
-      if (grp == 1) bp_ld4(p.aux0 + (int64_t)m * p.ld_aux0 + c, in.a0);          // x
-      break;
-    case GET_BPE_TANH_BLEND:
-      bp_ld4(p.aux0 + (int64_t)m * p.ld_aux0 + c, in.a0);                          // z
-      bp_ld4(p.aux1 + (int64_t)m * p.ld_aux1 + c, in.a1);                          // x
-      break;
-    case GET_BPE_TANH_ROWGROUP:
-      bp_ld4(p.aux0 + (int64_t)(m / p.group_rows) * p.ld_aux0 + c, in.a0);
-      break;
-    case GET_BPE_DGATE_R:
-      bp_ld4(p.aux0 + (int64_t)m * p.ld_aux0 + c, in.a0);                          // x
-      bp_ld4(p.aux1 + (int64_t)m * p.ld_aux1 + c, in.a1);                          // r
-      bp_ld4(p.out1 + (int64_t)m * p.ld_out1 + c, in.o);                           // dx
-      break;
-    default: break;
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void bp_epi_apply(const BpParams& p, int m, int n, int c, int grp, const float acc[4], const BpEpiIn& in) {
-  float v[4], o[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = acc[e];
-  if (p.bias) {
-    float b[4];
-    bp_ld4(p.bias + n, b);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] += b[e];
-  }
-  __nv_bfloat16* prow = p.planes ? p.planes + (int64_t)m * p.ld_p + c : nullptr;
-  switch (EPI) {
-    case GET_BPE_STORE: {
-      if (p.drop_thr) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool keep = drop_keep(p.drop_seed + __ldg(p.salt), (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + e), p.drop_thr);
-          v[e] = keep ? v[e] * p.drop_scale : 0.f;
-        }
-      }
-      if (p.accumulate) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] += in.o[e];
-      }
-      if (p.C) bp_st4(p.C + (int64_t)m * p.ldc + c, v);
-      if (prow) planes_store4(prow, p.plane_stride, p.nplanes, v);
-    } break;
-    case GET_BPE_ZR: {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = sigmoid_fast(v[e]);
-      if (grp == 0) {
-        bp_st4(p.C + (int64_t)m * p.ldc + c, v);
-      } else {
-        bp_st4(p.out1 + (int64_t)m * p.ld_out1 + c, v);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = v[e] * in.a0[e];
-        if (prow) planes_store4(prow, p.plane_stride, p.nplanes, o);
-      }
-    } break;
-    case GET_BPE_TANH_BLEND: {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        v[e] = tanh_fast(v[e]);
-        o[e] = v[e] * in.a0[e] + in.a1[e] * (1.0f - in.a0[e]);
-      }
-      if (p.out1) bp_st4(p.out1 + (int64_t)m * p.ld_out1 + c, v);
-      if (p.C) bp_st4(p.C + (int64_t)m * p.ldc + c, o);
-      if (prow) planes_store4(prow, p.plane_stride, p.nplanes, o);
-    } break;
-    case GET_BPE_TANH_ROWGROUP: {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = tanh_fast(v[e] + in.a0[e]);
-      bp_st4(p.C + (int64_t)m * p.ldc + c, v);
-      if (prow) planes_store4(prow, p.plane_stride, p.nplanes, v);
-    } break;
-    case GET_BPE_DGATE_R: {
-      float g[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        g[e] = v[e] * in.a0[e] * in.a1[e] * (1.0f - in.a1[e]);
-        o[e] = in.o[e] + v[e] * in.a1[e];
-      }
-      if (p.C) bp_st4(p.C + (int64_t)m * p.ldc + c, g);
-      if (prow) planes_store4(prow, p.plane_stride, p.nplanes, g);
-      bp_st4(p.out1 + (int64_t)m * p.ld_out1 + c, o);
-    } break;
-    case GET_BPE_TANH: {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = tanh_fast(v[e]);
-      bp_st4(p.C + (int64_t)m * p.ldc + c, v);
-      if (prow) planes_store4(prow, p.plane_stride, p.nplanes, v);
-    } break;
-    default: break;
-  }
-}
-
-// padding columns of the output planes: zeros, 1.0 in the first pad column when pad_one
-__device__ __forceinline__ void bp_epi_pad(const BpParams& p, int m, int c, int first_pad) {
-  float v[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = (p.pad_one && c + e == first_pad) ? 1.0f : 0.0f;
-  planes_store4(p.planes + (int64_t)m * p.ld_p + c, p.plane_stride, p.nplanes, v);
-}
 
 __device__ __forceinline__ void bp_locate(const BpCfg& cfg, int kb, int& seg, int& kin) {
   seg = 0;
   while (seg + 1 < cfg.nseg && kb >= cfg.kblocks[seg]) { kb -= cfg.kblocks[seg]; ++seg; }
   kin = kb * cfg.kb;
+}
+
+namespace tc {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+}  // namespace tc
+
+// 16 fp32 values of one row -> staging tile of 32 rows x 16 columns (64-byte rows, TMA SWIZZLE_64B pattern)
+__device__ __forceinline__ void bp_stage_f32(uint32_t tile, int lane, const float (&v)[16]) {
+  const uint32_t row = tile + (uint32_t)lane * 64u, sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tc::sts128f(row + (((uint32_t)q ^ sw) << 4), v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+}
+// 16 values -> nplanes bf16 staging tiles of 32 rows x 16 columns (32-byte rows, TMA SWIZZLE_32B pattern), 1 KB apart
+__device__ __forceinline__ void bp_stage_planes(uint32_t tile, int lane, int nplanes, float (&r)[16]) {
+  const uint32_t sw = (uint32_t)(lane >> 2) & 1u;
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    if (p < nplanes) {
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const __nv_bfloat16 q0 = __float2bfloat16_rn(r[2 * e]), q1 = __float2bfloat16_rn(r[2 * e + 1]);
+        w[e] = (uint32_t)__bfloat16_as_ushort(q0) | ((uint32_t)__bfloat16_as_ushort(q1) << 16);
+        r[2 * e] -= __bfloat162float(q0);
+        r[2 * e + 1] -= __bfloat162float(q1);
+      }
+      const uint32_t row = tile + (uint32_t)p * 1024u + (uint32_t)lane * 32u;
+      tc::sts128(row + ((0u ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+      tc::sts128(row + ((1u ^ sw) << 4), make_uint4(w[4], w[5], w[6], w[7]));
+    }
+  }
+}
+// 16 consecutive fp32 of one row (quads at or beyond `nvalid` columns read as zero)
+__device__ __forceinline__ void bp_ld16(const float* p, int nvalid, bool row_ok, float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_ok && q * 4 < nvalid) t = *reinterpret_cast<const float4*>(p + q * 4);
+    v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+  }
 }
 
 template <int EPI>
@@ -230,6 +151,13 @@ gemm_bp_kernel(const __grid_constant__ BpParams p, const __grid_constant__ BpCfg
   __shared__ __align__(8) uint64_t bar_accf[2];                // accumulator set complete (tcgen05.commit)
   __shared__ __align__(8) uint64_t bar_acce[2];                // accumulator set drained (all epilogue threads arrive)
   __shared__ uint32_t tmem_holder;
+#ifdef GETB_BP_TIMELINE   // compile with -DGETB_BP_TIMELINE and run with GET_B200_BP_DEBUG=9: per-role timeline of CTA 0
+  __shared__ long long dbg_ts[4][32];
+  const long long dbg_t0 = clock64();
+#define BP_DBG(role, idx) do { if (cfg.debug == 9 && blockIdx.x == 0 && (idx) < 32) dbg_ts[role][idx] = clock64() - dbg_t0; } while (0)
+#else
+#define BP_DBG(role, idx) do { } while (0)
+#endif
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = cfg.BN;
@@ -259,6 +187,9 @@ gemm_bp_kernel(const __grid_constant__ BpParams p, const __grid_constant__ BpCfg
   const uint32_t tmem_base = tmem_holder;
 
   const int n_my = ((int)blockIdx.x < cfg.items) ? (cfg.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int ntn = cfg.ntn, ntm = cfg.ntm, kb_per_split = cfg.kb_per_split, kblocks_total = cfg.kblocks_total;
+  const int nstages = cfg.stages;
+  const uint32_t stage_bytes = cfg.stage_bytes;
 
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
@@ -266,85 +197,117 @@ gemm_bp_kernel(const __grid_constant__ BpParams p, const __grid_constant__ BpCfg
       for (int s = 0; s < cfg.nseg; ++s) { prefetch_tmap(&maps.a[s]); prefetch_tmap(&maps.b[s]); }
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = cfg.a_bytes + cfg.b_bytes;
+      const uint32_t tx = cfg.a_bytes + cfg.b_bytes, a_bytes = cfg.a_bytes;
+      const int a_mn = cfg.a_mn, b_mn = cfg.b_mn, a_boxes = cfg.a_boxes, b_boxes = cfg.b_boxes;
+      const uint32_t a_box_bytes = cfg.a_box_bytes, b_box_bytes = cfg.b_box_bytes;
       for (int it = 0; it < n_my; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
-        const int nt = item % cfg.ntn, mt = (item / cfg.ntn) % cfg.ntm, z = item / (cfg.ntn * cfg.ntm);
+        const int nt = item % ntn, mt = (item / ntn) % ntm, z = item / (ntn * ntm);
         const int m0 = mt * BP_BM, n0 = nt * BN;
-        const int kb0 = z * cfg.kb_per_split, kb1 = min(cfg.kblocks_total, kb0 + cfg.kb_per_split);
+        const int kb0 = z * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+        int seg, kin;
+        bp_locate(cfg, kb0, seg, kin);
+        int seg_left = cfg.kblocks[seg] - kin / cfg.kb;      // k blocks left in the current segment
         for (int kb = kb0; kb < kb1; ++kb) {
-          int seg, kin;
-          bp_locate(cfg, kb, seg, kin);
           mbar_wait(&bar_empty[stage], phase ^ 1);
-          const uint32_t sa = smem_base + (uint32_t)stage * cfg.stage_bytes;
-          const uint32_t sb = sa + cfg.a_bytes;
+          if (kb == kb0) BP_DBG(0, it * 2);
+          if (kb == kb1 - 1) BP_DBG(0, it * 2 + 1);
+          if (it == 1 && kb - kb0 < 8) BP_DBG(0, 16 + (kb - kb0));
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
           mbar_arrive_expect_tx(&bar_full[stage], tx);
-          if (cfg.a_mn) {
-            for (int b = 0; b < cfg.a_boxes; ++b) tma_load_3d(sa + (uint32_t)b * cfg.a_box_bytes, &maps.a[seg], m0 + b * 64, kin, 0, &bar_full[stage]);
+          if (a_mn) {
+            for (int b = 0; b < a_boxes; ++b) tma_load_3d(sa + (uint32_t)b * a_box_bytes, &maps.a[seg], m0 + b * 64, kin, 0, &bar_full[stage]);
           } else {
             tma_load_3d(sa, &maps.a[seg], kin, m0, 0, &bar_full[stage]);
           }
-          if (cfg.b_mn) {
-            for (int b = 0; b < cfg.b_boxes; ++b) tma_load_3d(sb + (uint32_t)b * cfg.b_box_bytes, &maps.b[seg], n0 + b * 64, kin, 0, &bar_full[stage]);
+          if (b_mn) {
+            for (int b = 0; b < b_boxes; ++b) tma_load_3d(sb + (uint32_t)b * b_box_bytes, &maps.b[seg], n0 + b * 64, kin, 0, &bar_full[stage]);
           } else {
             tma_load_3d(sb, &maps.b[seg], kin, n0, 0, &bar_full[stage]);
           }
-          if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          kin += cfg.kb;
+          if (--seg_left == 0 && seg + 1 < cfg.nseg) { ++seg; kin = 0; seg_left = cfg.kblocks[seg]; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // =========================================== MMA issuer =============================================
+    // One thread issues everything, so its instruction count per tcgen05.mma is what bounds the tensor pipe at these
+    // tile sizes: the descriptors' constant halves are built once, per MMA only the 14-bit start-address field moves.
     if (lane == 0) {
       // kind::f16 instruction descriptor: D = f32, A = B = bf16, majors, N >> 3, M >> 4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cfg.a_mn ? 1 : 0) << 15) |
                              ((uint32_t)(cfg.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BP_BM >> 4) << 24);
-      const int ksteps = cfg.kb / 16;
+      const int ksteps = cfg.kb >> 4, mode = cfg.mode, acc_cols = cfg.acc_cols, acc_bufs = cfg.acc_bufs;
+      const uint64_t a_d0 = smem_desc(smem_base, cfg.a_lbo, cfg.a_sbo, cfg.a_lt);
+      const uint64_t b_d0 = smem_desc(smem_base + cfg.a_bytes, cfg.b_lbo, cfg.b_sbo, cfg.b_lt);
+      const uint32_t a_hi = (uint32_t)(a_d0 >> 32), b_hi = (uint32_t)(b_d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_d0, b_lo0 = (uint32_t)b_d0;
+      const uint32_t a_ks = cfg.a_kstep >> 4, b_ks = cfg.b_kstep >> 4, a_pl = cfg.a_plane >> 4, b_pl = cfg.b_plane >> 4;
+      const uint32_t stage16 = stage_bytes >> 4;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int it = 0; it < n_my; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
-        const int z = item / (cfg.ntn * cfg.ntm);
-        const int kb0 = z * cfg.kb_per_split, kb1 = min(cfg.kblocks_total, kb0 + cfg.kb_per_split);
+        const int z = item / (ntn * ntm);
+        const int kb0 = z * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
         mbar_wait(&bar_acce[acc], acc_phase ^ 1);
         fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(acc * cfg.acc_cols);
+        BP_DBG(1, it * 3);
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * acc_cols);
         const uint32_t d_small = d_main + (uint32_t)BN;
+        uint32_t first = 0u;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bar_full[stage], phase);
           fence_after();
-          const uint32_t sa = smem_base + (uint32_t)stage * cfg.stage_bytes;
-          const uint32_t sb = sa + cfg.a_bytes;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t a0 = sa + (uint32_t)ks * cfg.a_kstep, b0 = sb + (uint32_t)ks * cfg.b_kstep;
-            const uint64_t da0 = smem_desc(a0, cfg.a_lbo, cfg.a_sbo, cfg.a_lt);
-            const uint64_t db0 = smem_desc(b0, cfg.b_lbo, cfg.b_sbo, cfg.b_lt);
-            const uint32_t first = (kb > kb0 || ks > 0) ? 1u : 0u;
-            umma_bf16(d_main, da0, db0, idesc, first);
-            if (cfg.mode >= 2) {
-              const uint64_t da1 = smem_desc(a0 + cfg.a_plane, cfg.a_lbo, cfg.a_sbo, cfg.a_lt);
-              const uint64_t db1 = smem_desc(b0 + cfg.b_plane, cfg.b_lbo, cfg.b_sbo, cfg.b_lt);
-              if (cfg.mode == 2) {
-                umma_bf16(d_main, da0, db1, idesc, 1u);
-                umma_bf16(d_main, da1, db0, idesc, 1u);
-              } else {
-                const uint64_t da2 = smem_desc(a0 + 2u * cfg.a_plane, cfg.a_lbo, cfg.a_sbo, cfg.a_lt);
-                const uint64_t db2 = smem_desc(b0 + 2u * cfg.b_plane, cfg.b_lbo, cfg.b_sbo, cfg.b_lt);
-                umma_bf16(d_small, da0, db1, idesc, first);
-                umma_bf16(d_small, da1, db0, idesc, 1u);
-                umma_bf16(d_small, da1, db1, idesc, 1u);
-                umma_bf16(d_small, da0, db2, idesc, 1u);
-                umma_bf16(d_small, da2, db0, idesc, 1u);
+          if (kb == kb0) BP_DBG(1, it * 3 + 1);
+          if (it == 1 && kb - kb0 < 8) BP_DBG(3, (kb - kb0) * 2);
+          const uint32_t sa = a_lo0 + (uint32_t)stage * stage16, sb = b_lo0 + (uint32_t)stage * stage16;
+          if (mode == 1) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                umma_bf16(d_main, desc64(sa + ks * a_ks, a_hi), desc64(sb + ks * b_ks, b_hi), idesc, first);
+                first = 1u;
+              }
+            }
+          } else if (mode == 2) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                const uint32_t a0 = sa + ks * a_ks, b0 = sb + ks * b_ks;
+                umma_bf16(d_main, desc64(a0, a_hi), desc64(b0, b_hi), idesc, first);
+                umma_bf16(d_main, desc64(a0, a_hi), desc64(b0 + b_pl, b_hi), idesc, 1u);
+                umma_bf16(d_main, desc64(a0 + a_pl, a_hi), desc64(b0, b_hi), idesc, 1u);
+                first = 1u;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                const uint32_t a0 = sa + ks * a_ks, b0 = sb + ks * b_ks;
+                umma_bf16(d_main, desc64(a0, a_hi), desc64(b0, b_hi), idesc, first);
+                umma_bf16(d_small, desc64(a0, a_hi), desc64(b0 + b_pl, b_hi), idesc, first);
+                umma_bf16(d_small, desc64(a0 + a_pl, a_hi), desc64(b0, b_hi), idesc, 1u);
+                umma_bf16(d_small, desc64(a0 + a_pl, a_hi), desc64(b0 + b_pl, b_hi), idesc, 1u);
+                umma_bf16(d_small, desc64(a0, a_hi), desc64(b0 + 2u * b_pl, b_hi), idesc, 1u);
+                umma_bf16(d_small, desc64(a0 + 2u * a_pl, a_hi), desc64(b0, b_hi), idesc, 1u);
+                first = 1u;
               }
             }
           }
           umma_commit(&bar_empty[stage]);
-          if (++stage == cfg.stages) { stage = 0; phase ^= 1; }
+          if (it == 1 && kb - kb0 < 8) BP_DBG(3, (kb - kb0) * 2 + 1);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_accf[acc]);
-        if (cfg.acc_bufs == 2) {
+        BP_DBG(1, it * 3 + 2);
+        if (acc_bufs == 2) {
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         } else {
@@ -355,126 +318,223 @@ gemm_bp_kernel(const __grid_constant__ BpParams p, const __grid_constant__ BpCfg
     __syncwarp();
   } else {
     // =========================================== epilogue ===============================================
+    // TMEM hands every thread one output ROW. The fused math runs in that layout on 16-column pieces: the auxiliary
+    // operands are read row-wise (one 64-byte piece per thread and instruction: 2 KB in flight per warp instruction),
+    // the results are staged in swizzled shared-memory tiles and leave through TMA stores (coalesced, asynchronous,
+    // clipped at the tensor edges by the hardware), fp32 outputs and bf16 planes alike.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int chalf = (warp - 2) >> 2;            // two warps per quarter: even / odd 32-column chunks
-    const uint32_t stg = smem_base + (uint32_t)cfg.stages * cfg.stage_bytes + (uint32_t)(warp - 2) * (32u * BP_STG_LD * 4u);
-    const int rrow = lane >> 3, rq = lane & 7;
+    const int chalf = (warp - 2) >> 2;            // two warps per quarter: even / odd 16-column pieces
+    const uint32_t stg_set = cfg.stg_set;
+    const uint32_t stg0 = smem_base + (uint32_t)nstages * stage_bytes + (uint32_t)(warp - 2) * 2u * stg_set;
+    // tile offsets inside a staging set (fixed per launch): [C 2 KB][out1 2 KB][planes 1 KB each]; the fused z|r epilogue
+    // writes either z (C) or r (out1) + planes per piece, so its out1 tile shares the C slot
+    const uint32_t off_o1 = (EPI != GET_BPE_ZR && (p.has_c || cfg.splits > 1)) ? 2048u : 0u;
+    const uint32_t off_p = off_o1 + (p.has_o1 ? 2048u : 0u);
+    uint32_t set = 0;
     const bool small = cfg.mode == 3;
+    const int npieces = BN >> 4;
+    const int last_piece = (npieces - 1 >= chalf) ? ((npieces - 1 - chalf) / 2 * 2 + chalf) : -1;
+    const int splits = cfg.splits, acc_cols = cfg.acc_cols, acc_bufs = cfg.acc_bufs;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int it = 0; it < n_my; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
-      const int nt = item % cfg.ntn, mt = (item / cfg.ntn) % cfg.ntm, z = item / (cfg.ntn * cfg.ntm);
+      const int nt = item % ntn, mt = (item / ntn) % ntm, z = item / (ntn * ntm);
       const int m_base = mt * BP_BM + quarter * 32;
+      const int m = m_base + lane;
+      const bool row_ok = m < p.M;
       const int n0 = nt * BN;
       mbar_wait(&bar_accf[acc], acc_phase);
       fence_after();
-      const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * cfg.acc_cols);
+      if (warp == 2 && lane == 0) BP_DBG(2, it * 2);
+      const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols);
       const uint32_t t_small = t_main + (uint32_t)BN;
-      const int nch = (BN + 31) / 32;
-      const int last_col = (nch - 1 >= chalf) ? ((nch - 1 - chalf) / 2 * 2 + chalf) * 32 : -1;
-      if (last_col < 0) {                 // single-chunk tiles: the odd warps have nothing to read
+      if (last_piece < 0) {               // 16-column tiles: the odd warps have nothing to read
         fence_before();
         mbar_arrive(&bar_acce[acc]);
       }
-      for (int col = chalf * 32; col < BN; col += 64) {
-        const bool two = col + 16 < BN;
-        uint32_t rm[16], rs[16], rm2[16], rs2[16];
+      for (int pc = chalf; pc < npieces; pc += 2) {
+        const int col = pc << 4;
+        const int n = n0 + col;
+        uint32_t rm[16], rs[16];
         tmem_ld16_nowait(t_main + (uint32_t)col, rm);
         if (small) tmem_ld16_nowait(t_small + (uint32_t)col, rs);
-        if (two) {
-          tmem_ld16_nowait(t_main + (uint32_t)col + 16u, rm2);
-          if (small) tmem_ld16_nowait(t_small + (uint32_t)col + 16u, rs2);
+        // ---- where does this piece go? c = column inside the destination tensors, nv = valid columns of the piece
+        int grp = 0, c = n, nv = p.N - n, nvp = p.Npad - n;
+        if (EPI == GET_BPE_ZR) {
+          grp = n / p.zr_gs;
+          c = n - grp * p.zr_gs;
+          nv = grp > 1 ? 0 : p.zr_cols - c;
+          nvp = grp == 1 ? p.zr_cols_pad - c : 0;
+        }
+        nv = max(0, min(16, nv));
+        nvp = max(0, min(16, nvp));
+        // ---- auxiliary operands, row-wise (issued before the accumulator wait: the latencies overlap)
+        float a0[16], a1[16], o[16];
+        if (splits == 1) {
+          if (EPI == GET_BPE_STORE) {
+            if (p.accumulate) bp_ld16(p.C + (int64_t)m * p.ldc + c, nv, row_ok, o);
+          } else if (EPI == GET_BPE_ZR) {
+            if (grp == 1) bp_ld16(p.aux0 + (int64_t)m * p.ld_aux0 + c, nv, row_ok, a0);
+          } else if (EPI == GET_BPE_TANH_BLEND) {
+            bp_ld16(p.aux0 + (int64_t)m * p.ld_aux0 + c, nv, row_ok, a0);
+            bp_ld16(p.aux1 + (int64_t)m * p.ld_aux1 + c, nv, row_ok, a1);
+          } else if (EPI == GET_BPE_TANH_ROWGROUP) {
+            bp_ld16(p.aux0 + (int64_t)(m / p.group_rows) * p.ld_aux0 + c, nv, row_ok, a0);
+          } else if (EPI == GET_BPE_DGATE_R) {
+            bp_ld16(p.aux0 + (int64_t)m * p.ld_aux0 + c, nv, row_ok, a0);
+            bp_ld16(p.aux1 + (int64_t)m * p.ld_aux1 + c, nv, row_ok, a1);
+            bp_ld16(p.out1 + (int64_t)m * p.ld_out1 + c, nv, row_ok, o);
+          }
         }
         tmem_ld_wait();
-        if (!small) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) { rs[e] = 0u; rs2[e] = 0u; }
-        }
-        if (col == last_col) {           // last chunk of this accumulator set for this warp: hand it back to the MMA warp
+        if (pc == last_piece) {           // last piece of this accumulator set for this warp: hand it back to the MMA warp
           fence_before();
           mbar_arrive(&bar_acce[acc]);
         }
+        float v[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 v;
-          v.x = __float_as_uint(__uint_as_float(rm[q * 4 + 0]) + __uint_as_float(rs[q * 4 + 0]));
-          v.y = __float_as_uint(__uint_as_float(rm[q * 4 + 1]) + __uint_as_float(rs[q * 4 + 1]));
-          v.z = __float_as_uint(__uint_as_float(rm[q * 4 + 2]) + __uint_as_float(rs[q * 4 + 2]));
-          v.w = __float_as_uint(__uint_as_float(rm[q * 4 + 3]) + __uint_as_float(rs[q * 4 + 3]));
-          sts128(stg + (uint32_t)(lane * BP_STG_LD + q * 4) * 4u, v);
+        for (int e = 0; e < 16; ++e) v[e] = small ? __uint_as_float(rm[e]) + __uint_as_float(rs[e]) : __uint_as_float(rm[e]);
+        // the stores issued from this staging set (two pieces ago) must have finished READING it before it is overwritten
+        const uint32_t stg_c = stg0 + set * stg_set, stg_o1 = stg_c + off_o1, stg_p = stg_c + off_p;
+        set ^= 1u;
+        if (lane == 0) bulk_wait_read1();
+        __syncwarp();
+        if (splits > 1) {
+          bp_stage_f32(stg_c, lane, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&maps.c, stg_c, n, m_base, z);
+            bulk_commit();
+          }
+          continue;
         }
-        if (two) {
+        if (nv == 0 && nvp == 0) {
+          if (lane == 0) bulk_commit();    // keep one bulk group per piece: the wait above counts groups
+          continue;
+        }
+        if (p.bias) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 v;
-            v.x = __float_as_uint(__uint_as_float(rm2[q * 4 + 0]) + __uint_as_float(rs2[q * 4 + 0]));
-            v.y = __float_as_uint(__uint_as_float(rm2[q * 4 + 1]) + __uint_as_float(rs2[q * 4 + 1]));
-            v.z = __float_as_uint(__uint_as_float(rm2[q * 4 + 2]) + __uint_as_float(rs2[q * 4 + 2]));
-            v.w = __float_as_uint(__uint_as_float(rm2[q * 4 + 3]) + __uint_as_float(rs2[q * 4 + 3]));
-            sts128(stg + (uint32_t)(lane * BP_STG_LD + 16 + q * 4) * 4u, v);
+            if (q * 4 < nv) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+              v[q * 4 + 0] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+            }
           }
         }
-        __syncwarp();
-        const int n = n0 + col + rq * 4;
-        if (two || rq < 4) {
-          if (cfg.splits > 1) {
-            if (n < (int)p.ws_ld) {
+        bool st_c = false, st_o1 = false, st_p = false;
+        float w[16];                       // values for the planes
+        if (EPI == GET_BPE_STORE) {
+          if (p.drop_thr) {
+            const uint32_t sd = p.drop_seed + __ldg(p.salt);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int row = i * 4 + rrow;
-                const int m = m_base + row;
-                if (m < p.M) {
-                  const float4 f = lds128(stg + (uint32_t)(row * BP_STG_LD + rq * 4) * 4u);
-                  *reinterpret_cast<float4*>(p.workspace + ((int64_t)z * p.M + m) * p.ws_ld + n) = f;
-                }
-              }
-            }
+            for (int e = 0; e < 16; ++e)
+              v[e] = drop_keep(sd, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + e), p.drop_thr) ? v[e] * p.drop_scale : 0.f;
+          }
+          if (p.accumulate) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += o[e];
+          }
+          st_c = p.has_c && nv > 0;
+          if (st_c) bp_stage_f32(stg_c, lane, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) w[e] = v[e];
+          st_p = p.has_pl;
+        } else if (EPI == GET_BPE_ZR) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = sigmoid_fast(v[e]);
+          if (grp == 0) {
+            st_c = nv > 0;
+            if (st_c) bp_stage_f32(stg_c, lane, v);
           } else {
-            int c, grp;
-            const int kind = bp_quad_kind<EPI>(p, n, c, grp);
-            if (kind == 1) {
+            st_o1 = nv > 0;
+            if (st_o1) bp_stage_f32(stg_o1, lane, v);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {          // two batches of four rows: all loads first, then math + stores
-                BpEpiIn in[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int m = m_base + (h * 4 + i) * 4 + rrow;
-                  if (m < p.M) bp_epi_load<EPI>(p, m, c, grp, in[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int row = (h * 4 + i) * 4 + rrow;
-                  const int m = m_base + row;
-                  if (m < p.M) {
-                    const float4 f = lds128(stg + (uint32_t)(row * BP_STG_LD + rq * 4) * 4u);
-                    const float v[4] = {f.x, f.y, f.z, f.w};
-                    bp_epi_apply<EPI>(p, m, n, c, grp, v, in[i]);
-                  }
-                }
-              }
-            } else if (kind == 2) {
-              const int first_pad = (EPI == GET_BPE_ZR) ? p.zr_cols : p.N;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int m = m_base + i * 4 + rrow;
-                if (m < p.M) bp_epi_pad(p, m, c, first_pad);
-              }
-            }
+            for (int e = 0; e < 16; ++e) w[e] = v[e] * a0[e];
+            st_p = p.has_pl;
           }
+        } else if (EPI == GET_BPE_TANH_BLEND) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            v[e] = tanh_fast(v[e]);
+            w[e] = v[e] * a0[e] + a1[e] * (1.0f - a0[e]);
+          }
+          st_o1 = p.has_o1 && nv > 0;
+          if (st_o1) bp_stage_f32(stg_o1, lane, v);
+          st_c = p.has_c && nv > 0;
+          if (st_c) bp_stage_f32(stg_c, lane, w);
+          st_p = p.has_pl;
+        } else if (EPI == GET_BPE_TANH_ROWGROUP) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { v[e] = tanh_fast(v[e] + a0[e]); w[e] = v[e]; }
+          st_c = nv > 0;
+          if (st_c) bp_stage_f32(stg_c, lane, v);
+          st_p = p.has_pl;
+        } else if (EPI == GET_BPE_DGATE_R) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            w[e] = v[e] * a0[e] * a1[e] * (1.0f - a1[e]);
+            o[e] += v[e] * a1[e];
+          }
+          st_c = p.has_c && nv > 0;
+          if (st_c) bp_stage_f32(stg_c, lane, w);
+          st_o1 = nv > 0;
+          if (st_o1) bp_stage_f32(stg_o1, lane, o);
+          st_p = p.has_pl;
+        } else {   // GET_BPE_TANH
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { v[e] = tanh_fast(v[e]); w[e] = v[e]; }
+          st_c = nv > 0;
+          if (st_c) bp_stage_f32(stg_c, lane, v);
+          st_p = p.has_pl;
         }
+        st_p = st_p && nvp > 0;
+        if (st_p) {
+          // columns at or beyond the logical width are padding: zeros, 1.0 in the first pad column when pad_one
+          if (nv < 16) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e >= nv) w[e] = (p.pad_one && e == nv) ? 1.0f : 0.0f;
+          }
+          bp_stage_planes(stg_p, lane, p.nplanes, w);
+        }
+        fence_proxy_async();               // generic-proxy stores -> visible to the TMA engine
         __syncwarp();
+        if (lane == 0) {
+          if (st_c) tma_store_2d(&maps.c, stg_c, c, m_base);
+          if (st_o1) tma_store_2d(&maps.o1, stg_o1, c, m_base);
+          if (st_p) {
+            for (int pl = 0; pl < p.nplanes; ++pl) tma_store_3d(&maps.pl, stg_p + (uint32_t)pl * 1024u, c, m_base, pl);
+          }
+          bulk_commit();
+        }
       }
-      if (cfg.acc_bufs == 2) {
+      if (warp == 2 && lane == 0) BP_DBG(2, it * 2 + 1);
+      if (acc_bufs == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       } else {
         acc_phase ^= 1;
       }
     }
+    if (lane == 0) bulk_wait_read0();     // shared memory must outlive the last stores' reads
+    __syncwarp();
   }
   fence_before();
   __syncthreads();
+#ifdef GETB_BP_TIMELINE
+  if (cfg.debug == 9 && blockIdx.x == 0 && tid == 0) {
+    printf("BPDBG cfg BN=%d kb=%d stages=%d mode=%d items=%d kblocks=%d a_mn=%d stage_bytes=%u\n", cfg.BN, cfg.kb, cfg.stages, cfg.mode,
+           cfg.items, cfg.kblocks_total, cfg.a_mn, cfg.stage_bytes);
+    for (int it = 0; it < n_my && it < 5; ++it)
+      printf("BPDBG it=%d prod[%lld %lld] mma[acce %lld first_full %lld last_commit %lld] epi[%lld %lld]\n", it, dbg_ts[0][it * 2],
+             dbg_ts[0][it * 2 + 1], dbg_ts[1][it * 3], dbg_ts[1][it * 3 + 1], dbg_ts[1][it * 3 + 2], dbg_ts[2][it * 2], dbg_ts[2][it * 2 + 1]);
+    for (int j = 0; j < 8; ++j)
+      printf("BPDBG it=1 kb=%d tma_issue %lld | mma full_seen %lld issued %lld\n", j, dbg_ts[0][16 + j], dbg_ts[3][j * 2], dbg_ts[3][j * 2 + 1]);
+    printf("BPDBG end %lld\n", clock64() - dbg_t0);
+  }
+#endif
   if (warp == 1) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg.tmem_cols) : "memory");
@@ -514,7 +574,8 @@ __global__ void __launch_bounds__(256) to_planes_kernel(const float* __restrict_
   const int r = (int)(q / nq), c = (int)(q % nq) * 4;
   float v[4];
   if (vec && c + 4 <= cols) {
-    bp_ld4(src + (int64_t)r * ld_src + c, v);
+    const float4 t = *reinterpret_cast<const float4*>(src + (int64_t)r * ld_src + c);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = (c + e < cols) ? src[(int64_t)r * ld_src + c + e] : ((pad_one && c + e == cols) ? 1.0f : 0.0f);
@@ -570,10 +631,10 @@ static EncodeTiledFnBp bp_encode_fn() {
 struct BpMapKey {
   const void* ptr;
   int64_t d0, d1, d2, ld, ps;
-  int b0, b1, b2, sw;
+  int b0, b1, b2, sw, f32, rank;
   bool operator==(const BpMapKey& o) const {
     return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && ps == o.ps && b0 == o.b0 && b1 == o.b1 &&
-           b2 == o.b2 && sw == o.sw;
+           b2 == o.b2 && sw == o.sw && f32 == o.f32 && rank == o.rank;
   }
 };
 struct BpMapKeyHash {
@@ -581,17 +642,19 @@ struct BpMapKeyHash {
     uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
     h ^= (uint64_t)k.d0 * 0xC2B2AE3D27D4EB4Full + (uint64_t)k.d1 * 0x165667B19E3779F9ull + (uint64_t)k.d2 * 0x27D4EB2F165667C5ull;
     h ^= (uint64_t)k.ld * 31 + (uint64_t)k.ps * 131 + (uint64_t)k.b0 * 7 + (uint64_t)k.b1 * 1315423911ull + (uint64_t)k.b2 * 2654435761ull +
-         (uint64_t)k.sw * 97;
+         (uint64_t)k.sw * 97 + (uint64_t)k.f32 * 1009 + (uint64_t)k.rank * 7919;
     return (size_t)(h ^ (h >> 29));
   }
 };
 
-// 3-D bf16 tensor map {d0 inner contiguous, d1 rows `ld` apart, d2 planes `ps` apart}, box {b0, b1, b2}; sw: 64 or 128
-static bool bp_make_map(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t ld, int64_t ps, int b0,
-                        int b1, int b2, int sw) {
+// Tensor map over {d0 inner contiguous, d1 rows `ld` elements apart[, d2 slices `ps` elements apart]}, box {b0, b1[, b2]};
+// elements bf16 (f32 = 0) or fp32 (f32 = 1); sw = swizzle span in bytes (32 / 64 / 128). Encoding is memoised: the
+// allocator hands the same activation addresses back step after step.
+static bool bp_make_map(CUtensorMap* map, const void* ptr, int f32, int rank, int64_t d0, int64_t d1, int64_t d2, int64_t ld,
+                        int64_t ps, int b0, int b1, int b2, int sw) {
   static std::mutex mu;
   static std::unordered_map<BpMapKey, CUtensorMap, BpMapKeyHash> cache;
-  const BpMapKey key{ptr, d0, d1, d2, ld, ps, b0, b1, b2, sw};
+  const BpMapKey key{ptr, d0, d1, d2, ld, ps, b0, b1, b2, sw, f32, rank};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) {
@@ -599,17 +662,22 @@ static bool bp_make_map(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d
     return true;
   }
   EncodeTiledFnBp enc = bp_encode_fn();
-  if (!enc) return false;
+  if (!enc) {
+    set_error("get_gemm_bp: cuTensorMapEncodeTiled is not available");
+    return false;
+  }
+  const uint64_t es = f32 ? 4u : 2u;
   cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
-  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2u, (cuuint64_t)(d2 > 1 ? ps : ld * d1) * 2u};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * es, (cuuint64_t)(d2 > 1 ? ps : ld * d1) * es};
   cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  const CUtensorMapSwizzle swz = sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUresult rc = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                          const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
-    set_error("get_gemm_bp: cuTensorMapEncodeTiled failed (%d): dims %lld %lld %lld ld %lld ps %lld box %d %d %d", (int)rc,
-              (long long)d0, (long long)d1, (long long)d2, (long long)ld, (long long)ps, b0, b1, b2);
+    set_error("get_gemm_bp: cuTensorMapEncodeTiled failed (%d): rank %d f32 %d dims %lld %lld %lld ld %lld ps %lld box %d %d %d", (int)rc,
+              rank, f32, (long long)d0, (long long)d1, (long long)d2, (long long)ld, (long long)ps, b0, b1, b2);
     return false;
   }
   if (cache.size() > 8192) cache.clear();
@@ -640,7 +708,8 @@ static int bp_choose_bn(int M, int Npad, int mode, int splits) {
     const int64_t rounds = (items + BP_SMS - 1) / BP_SMS;
     const bool dbl = 2 * acc_cols <= 512;
     const uint32_t stage = (uint32_t)(BP_BM + bn) * np * 64u;
-    if ((224 * 1024 - BP_STG_BYTES - 2048) / (int)stage < 3) continue;
+    const int stg_bytes = BP_EPI_WARPS * 2 * (mode == 3 ? 5120 : 6144);   // largest staging the mode is used with
+    if ((226 * 1024 - stg_bytes - 1024) / (int)stage < 3) continue;
     const double l2 = (double)(BP_BM + bn) * np * 2.0 / 40.0;
     const double mma = (double)nmma * bn / 32.0;
     const double epi = 3.0 + bn / 16.0;            // in units comparable to one k element of a 300-deep contraction
@@ -682,13 +751,19 @@ static int bp_plan(const get_gemm_bp_desc* d, BpCfg& cfg, BpParams& p) {
   p.Npad = d->planes_out ? bp_round_up(d->N, 8) : d->N;
   p.epilogue = d->epilogue; p.accumulate = d->accumulate;
   p.C = d->C; p.ldc = d->ldc; p.out1 = d->out1; p.ld_out1 = d->ld_out1;
+  p.has_c = d->C != nullptr; p.has_o1 = d->out1 != nullptr; p.has_pl = d->planes_out != nullptr;
   p.bias = d->bias; p.aux0 = d->aux0; p.ld_aux0 = d->ld_aux0; p.aux1 = d->aux1; p.ld_aux1 = d->ld_aux1;
-  p.planes = reinterpret_cast<__nv_bfloat16*>(d->planes_out);
-  p.ld_p = d->ld_planes_out; p.plane_stride = d->planes_out_stride;
   p.nplanes = d->planes_out_n; p.pad_one = d->planes_out_pad_one;
   p.group_rows = d->group_rows; p.zr_gs = d->zr_group_stride; p.zr_cols = d->zr_cols;
   p.zr_cols_pad = bp_round_up(d->zr_cols, 8);
   p.salt = dropout_salt_ptr();
+  {
+    const int npl = p.has_pl ? p.nplanes : 0;
+    int kb_set = d->epilogue == GET_BPE_ZR ? 2 + npl : 2 * p.has_c + 2 * p.has_o1 + npl;
+    if (d->split_k > 1 || kb_set < 2) kb_set = 2;
+    GETB_REQUIRE(kb_set * 1024 <= BP_STG_SET_MAX, "get_gemm_bp: C + out1 + planes_out exceed the epilogue staging set (drop one output)");
+    cfg.stg_set = (uint32_t)kb_set * 1024u;
+  }
   GETB_REQUIRE(d->drop_out_p >= 0.f && d->drop_out_p < 1.f, "get_gemm_bp: dropout probability must be in [0,1)");
   if (d->drop_out_p > 0.f) {
     GETB_REQUIRE(d->epilogue == GET_BPE_STORE, "get_gemm_bp: dropout-out belongs to the STORE epilogue");
@@ -701,14 +776,15 @@ static int bp_plan(const get_gemm_bp_desc* d, BpCfg& cfg, BpParams& p) {
   GETB_REQUIRE(ok4(p.C, p.ldc) && ok4(p.out1, p.ld_out1) && ok4(p.aux0, p.ld_aux0) && ok4(p.aux1, p.ld_aux1) &&
                    (p.bias == nullptr || aligned16(p.bias)),
                "get_gemm_bp: fp32 epilogue tensors must be 16-byte aligned with ld %% 4 == 0");
-  if (p.planes) {
-    GETB_REQUIRE((((uintptr_t)p.planes) & 7u) == 0 && (p.ld_p % 4) == 0 && (p.plane_stride % 4) == 0 && p.nplanes >= 1 && p.nplanes <= 3,
-                 "get_gemm_bp: planes_out must be 8-byte aligned, ld %% 4 == 0, 1..3 planes");
+  if (d->planes_out) {
+    GETB_REQUIRE(aligned16(d->planes_out) && (d->ld_planes_out % 8) == 0 && (p.nplanes == 1 || (d->planes_out_stride % 8) == 0) &&
+                     p.nplanes >= 1 && p.nplanes <= 3,
+                 "get_gemm_bp: planes_out must be 16-byte aligned with ld %% 8 == 0, plane stride %% 8 == 0, 1..3 planes");
   }
   switch (d->epilogue) {
-    case GET_BPE_STORE: GETB_REQUIRE(p.C || p.planes || d->split_k > 1, "get_gemm_bp: STORE needs C or planes_out"); GETB_REQUIRE(!p.accumulate || p.C, "get_gemm_bp: accumulate needs C"); break;
+    case GET_BPE_STORE: GETB_REQUIRE(p.C || p.has_pl || d->split_k > 1, "get_gemm_bp: STORE needs C or planes_out"); GETB_REQUIRE(!p.accumulate || p.C, "get_gemm_bp: accumulate needs C"); break;
     case GET_BPE_ZR:
-      GETB_REQUIRE(p.C && p.out1 && p.zr_gs > 0 && p.zr_cols > 0 && (p.zr_cols % 4) == 0 && p.zr_cols <= p.zr_gs && (!p.planes || p.aux0),
+      GETB_REQUIRE(p.C && p.out1 && p.zr_gs > 0 && p.zr_cols > 0 && (p.zr_cols % 4) == 0 && p.zr_cols <= p.zr_gs && (!p.has_pl || p.aux0),
                    "get_gemm_bp: ZR needs C (z), out1 (r), zr_group_stride >= zr_cols, aux0 (x) with planes_out");
       break;
     case GET_BPE_TANH_BLEND: GETB_REQUIRE(p.aux0 && p.aux1, "get_gemm_bp: TANH_BLEND needs aux0 (z) and aux1 (x)"); break;
@@ -736,10 +812,9 @@ static int bp_plan(const get_gemm_bp_desc* d, BpCfg& cfg, BpParams& p) {
   while (tc < cfg.acc_bufs * cfg.acc_cols) tc <<= 1;
   cfg.tmem_cols = tc;
   if (cfg.splits > 1) {
-    p.ws_ld = (int64_t)cfg.ntn * bn;
-    p.workspace = d->workspace;
-    GETB_REQUIRE(d->workspace && d->workspace_floats >= (int64_t)cfg.splits * d->M * p.ws_ld,
-                 "get_gemm_bp: split-K workspace too small (%lld floats needed)", (long long)((int64_t)cfg.splits * d->M * p.ws_ld));
+    const int64_t ws_ld = (int64_t)cfg.ntn * bn;
+    GETB_REQUIRE(d->workspace && d->workspace_floats >= (int64_t)cfg.splits * d->M * ws_ld,
+                 "get_gemm_bp: split-K workspace too small (%lld floats needed)", (long long)((int64_t)cfg.splits * d->M * ws_ld));
     GETB_REQUIRE(aligned16(d->workspace), "get_gemm_bp: workspace must be 16-byte aligned");
   }
   // shared-memory geometry
@@ -777,12 +852,14 @@ static int bp_plan(const get_gemm_bp_desc* d, BpCfg& cfg, BpParams& p) {
       if (cfg.b_mn) { const uint32_t t = cfg.b_lbo; cfg.b_lbo = cfg.b_sbo; cfg.b_sbo = t; }
     }
   }
-  int stages = (225 * 1024 - BP_STG_BYTES - 1024) / (int)cfg.stage_bytes;
+  const int stg_bytes = BP_EPI_WARPS * 2 * (int)cfg.stg_set;
+  int stages = (226 * 1024 - stg_bytes - 1024) / (int)cfg.stage_bytes;
   if (stages > BP_MAX_STAGES) stages = BP_MAX_STAGES;
   const int cap = bp_env_int("GET_B200_BP_STAGES", 0);
   if (cap > 0 && stages > cap) stages = cap;
   GETB_REQUIRE(stages >= 2, "get_gemm_bp: tile (mode %d, tile_n %d, kblock %d) does not fit shared memory", d->mode, bn, kb);
   cfg.stages = stages;
+  cfg.debug = bp_env_int("GET_B200_BP_DEBUG", 0);
   return 0;
 }
 
@@ -799,14 +876,28 @@ static int bp_launch(const get_gemm_bp_desc* d, cudaStream_t st) {
   for (int s = 0; s < d->nseg; ++s) {
     const get_bp_tensor &A = d->A[s], &B = d->B[s];
     bool ok;
-    if (cfg.a_mn) ok = bp_make_map(&maps.a[s], A.ptr, d->M, d->K[s], np, A.ld, A.plane_stride, 64, kb, np, 128);
-    else ok = bp_make_map(&maps.a[s], A.ptr, d->K[s], d->M, np, A.ld, A.plane_stride, kb, BP_BM, np, kb == 64 ? 128 : 64);
+    if (cfg.a_mn) ok = bp_make_map(&maps.a[s], A.ptr, 0, 3, d->M, d->K[s], np, A.ld, A.plane_stride, 64, kb, np, 128);
+    else ok = bp_make_map(&maps.a[s], A.ptr, 0, 3, d->K[s], d->M, np, A.ld, A.plane_stride, kb, BP_BM, np, kb == 64 ? 128 : 64);
     if (!ok) return -3;
-    if (cfg.b_mn) ok = bp_make_map(&maps.b[s], B.ptr, d->N, d->K[s], np, B.ld, B.plane_stride, 64, kb, np, 128);
-    else ok = bp_make_map(&maps.b[s], B.ptr, d->K[s], d->N, np, B.ld, B.plane_stride, kb, cfg.BN, np, kb == 64 ? 128 : 64);
+    if (cfg.b_mn) ok = bp_make_map(&maps.b[s], B.ptr, 0, 3, d->N, d->K[s], np, B.ld, B.plane_stride, 64, kb, np, 128);
+    else ok = bp_make_map(&maps.b[s], B.ptr, 0, 3, d->K[s], d->N, np, B.ld, B.plane_stride, kb, cfg.BN, np, kb == 64 ? 128 : 64);
     if (!ok) return -3;
   }
-  const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + BP_STG_BYTES + 1024;
+  // output maps: the epilogue leaves through TMA stores of 32-row x 16-column pieces (clipped at the tensor edges)
+  const bool zr = d->epilogue == GET_BPE_ZR;
+  if (cfg.splits > 1) {
+    const int64_t ws_ld = (int64_t)cfg.ntn * cfg.BN;
+    if (!bp_make_map(&maps.c, d->workspace, 1, 3, ws_ld, d->M, cfg.splits, ws_ld, (int64_t)d->M * ws_ld, 16, 32, 1, 64)) return -3;
+  } else {
+    const int64_t ncols = zr ? d->zr_cols : d->N;
+    if (d->C && !bp_make_map(&maps.c, d->C, 1, 2, ncols, d->M, 1, d->ldc, 0, 16, 32, 1, 64)) return -3;
+    if (d->out1 && !bp_make_map(&maps.o1, d->out1, 1, 2, ncols, d->M, 1, d->ld_out1, 0, 16, 32, 1, 64)) return -3;
+    if (d->planes_out &&
+        !bp_make_map(&maps.pl, d->planes_out, 0, 3, zr ? p.zr_cols_pad : p.Npad, d->M, d->planes_out_n, d->ld_planes_out,
+                     d->planes_out_stride, 16, 32, 1, 32))
+      return -3;
+  }
+  const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + (size_t)BP_EPI_WARPS * 2 * cfg.stg_set + 1024;
   static const BpKernelFn kernels[6] = {gemm_bp_kernel<0>, gemm_bp_kernel<1>, gemm_bp_kernel<2>,
                                         gemm_bp_kernel<3>, gemm_bp_kernel<4>, gemm_bp_kernel<5>};
   const int epi = cfg.splits > 1 ? 0 : p.epilogue;

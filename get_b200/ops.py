@@ -247,9 +247,12 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
     fp32 SIMT kernel runs. exact=True pins the contraction to the fp32-exact class (the GSL top-k chain)."""
     lib = _lib.load()
     M, N = out.shape
-    want_tc = (tc and TC_ENABLED and M >= 128 and N % 4 == 0 and N >= 8 and alpha == 1.0 and rowidx is None and drop_p == 0.0
-               and epilogue in _BPE_OF and aux1 is None and out1 is None and out.stride(1) == 1 and out.stride(0) % 4 == 0
-               and (not presplit or all(b.shape[1] >= 8 for _, b in segments)))
+    has_planes = any(isinstance(a, Planes) or isinstance(b, Planes) for a, b in segments)
+    want_tc = (tc and TC_ENABLED and (M >= 128 or has_planes) and N % 4 == 0 and N >= 8 and alpha == 1.0 and rowidx is None
+               and drop_p == 0.0 and epilogue in _BPE_OF and aux1 is None and out1 is None and out.stride(1) == 1
+               and out.stride(0) % 4 == 0 and (not presplit or all(b.shape[1] >= 8 for _, b in segments)))
+    if has_planes and not want_tc:
+        raise RuntimeError("get_b200.gemm: plane operands need the tensor-core route (N %% 4 == 0, N >= 8, store/tanh epilogue)")
     if DEBUG_TC_REPORT:
         global LAST_GEMM_USED_TC
         LAST_GEMM_USED_TC = 2 if want_tc else 0

@@ -295,6 +295,24 @@ def gemm_bp(segments: Sequence[Tuple[Planes, Planes, int]], M: int, N: int, *, m
     return d
 
 
+def _wgrad_tile_n(M: int, N: int, kblocks: int) -> int:
+    """N tile of a weight-gradient contraction: few large output tiles, the long contraction split over the SMs. Cost model:
+    rounds x k blocks per item x bytes per k block (the MN-major B operand is loaded in 64-column boxes)."""
+    best, best_cost = 16, None
+    ntm = (M + 127) // 128
+    for bn in range(16, 257, 16):
+        nt = (N + bn - 1) // bn
+        if (nt - 1) * bn >= N:
+            continue
+        tiles = ntm * nt
+        splits = max(1, min(kblocks, _SM_COUNT // tiles if tiles <= _SM_COUNT else 1))
+        rounds = (tiles * splits + _SM_COUNT - 1) // _SM_COUNT
+        cost = rounds * ((kblocks + splits - 1) // splits) * (128 + 64 * ((bn + 63) // 64) + 24)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
 def wgrad_bp(a: Planes, b: Planes, M: int, N: int, K: int, mode: int, dsts, accumulate: bool, tn: int = 0):
     """Weight gradient  W[m,n] = sum_k a(m,k) b(n,k)  with both operands MN-major (stored (K, .) row-major), split over k
     across the SMs; `dsts` = [(dst fp32 2-D view or 1-D vector, row0, nrows, col0, ncols)] receive blocks of the result
@@ -306,9 +324,9 @@ def wgrad_bp(a: Planes, b: Planes, M: int, N: int, K: int, mode: int, dsts, accu
     for dst, t in ((d.A[0], a), (d.B[0], b)):
         dst.ptr, dst.ld, dst.plane_stride, dst.planes, dst.trans = t.ptr, t.ld, t.plane_stride, t.nplanes, t.trans
     d.K[0], d.M, d.N, d.mode, d.tile_n, d.epilogue = int(K), int(M), int(N), int(mode), int(tn), BPE_STORE
-    bn = tn or tile_n(M, N, mode)
-    tiles = ((M + 127) // 128) * ((round_up(N, 8) + bn - 1) // bn)
     kblocks = (K + 31) // 32
+    bn = tn or _wgrad_tile_n(M, N, kblocks)
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
     want = max(1, _SM_COUNT // tiles)
     d.split_k = min(kblocks, max(2, min(want, max(1, kblocks // 4))))      # >= 2 splits: one code path (partials + reduce)
     d.tile_n = bn
