@@ -89,18 +89,23 @@ SIGNATURES = {
     "get_gsl_mask_adj_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "get_att_pool_fwd_f32": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
     "get_att_pool_bwd_f32": (_I, [_P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _I, _P]),
+    "get_att_pool_bwd_bp": (_I, [_P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _L, _L, _I, _P, _P, _L, _I, _P]),
     "get_ggnn_gate_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
     "get_colsum_f32": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "get_colsum_workspace_floats": (_L, [_I, _I]),
     "get_rows_gather_f32": (_I, [_P, _L, _P, _I, _I, _P, _L, _P]),
     "get_rows_scatter_f32": (_I, [_P, _L, _P, _I, _I, _P, _L, _P]),
     "get_segment_sum_f32": (_I, [_P, _L, _P, _I, _I, _P, _L, _P]),
+    "get_segments_i32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "get_ids_mask_u8": (_I, [_P, _I, _L, _I, _P, _P]),
+    "get_embedding_rows_fwd_f32": (_I, [_P, _I, _I, _P, _I, _P, _L, _P]),
+    "get_embedding_rows_bwd_f32": (_I, [_P, _L, _P, _I, _I, _I, _P, _I, _P]),
     "get_masked_mean_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "get_masked_mean_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "get_dropout_mask_f32": (_I, [_P, _L, _F, _U, _P]),
     "get_rows_gather_dropout_f32": (_I, [_P, _L, _P, _I, _I, _F, _U, _P, _L, _P]),
     "get_ggnn_gate_bwd_bp": (_I, [_P, _P, _P, _P, _I, _I, _P, _L, _L, _I, _I, _I, _P, _P]),
-    "get_rows_gather_dropout_bp": (_I, [_P, _L, _P, _I, _I, _F, _U, _P, _L, _L, _I, _P]),
+    "get_rows_gather_dropout_bp": (_I, [_P, _L, _I, _P, _I, _I, _F, _U, _P, _L, _L, _I, _P]),
     "get_dropout_salt_set": (_I, [_U, _P]),
     "get_dropout_salt_advance": (_I, [_P]),
     "get_dropout_salt_get": (_I, [C.POINTER(C.c_uint32)]),

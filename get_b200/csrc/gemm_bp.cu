@@ -584,8 +584,11 @@ __global__ void __launch_bounds__(256) to_planes_kernel(const float* __restrict_
 }
 
 // ---- weight packing: many (strided) matrices -> 3 planes each, plus fused bias vectors, one launch -------------------
+// One block per 32 x 32 tile of a job (kind 0) or per 1024 elements of a bias vector (kind 1). Transposed views
+// (ld_r == 1) are read along their contiguous index and turned through shared memory, so reads and writes are coalesced
+// whatever the orientation of the packed weight.
 __global__ void __launch_bounds__(256) pack_planes_multi_kernel(const get_pack_job* __restrict__ jobs, int n_jobs) {
-  // binary search for the job covering this block
+  __shared__ float tile[32][33];
   int lo = 0, hi = n_jobs - 1;
   const int64_t blk = blockIdx.x;
   while (lo < hi) {
@@ -593,20 +596,38 @@ __global__ void __launch_bounds__(256) pack_planes_multi_kernel(const get_pack_j
     if (jobs[mid].first_block <= blk) lo = mid; else hi = mid - 1;
   }
   const get_pack_job j = jobs[lo];
-  const int64_t e = (blk - j.first_block) * 256 + threadIdx.x;
+  const int64_t lb = blk - j.first_block;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (j.kind == 1) {
-    if (e < j.rows) reinterpret_cast<float*>(j.dst)[e] = j.src[e] + (j.src2 ? j.src2[e] : 0.f);
+    for (int e = (int)lb * 1024 + threadIdx.x; e < min(j.rows, (int)(lb + 1) * 1024); e += 256)
+      reinterpret_cast<float*>(j.dst)[e] = j.src[e] + (j.src2 ? j.src2[e] : 0.f);
     return;
   }
-  if (e >= (int64_t)j.rows * j.cols) return;
-  const int r = (int)(e / j.cols), c = (int)(e % j.cols);
-  float v = j.src[(int64_t)r * j.ld_r + (int64_t)c * j.ld_c];
-  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(j.dst) + (int64_t)r * j.ld_out + c;
+  const int tiles_c = (j.cols + 31) >> 5;
+  const int r0 = (int)(lb / tiles_c) * 32, c0 = (int)(lb % tiles_c) * 32;
+  const bool by_rows = j.ld_r == 1 && j.ld_c != 1;      // the source is contiguous along r: read with threads along r
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    const __nv_bfloat16 q = __float2bfloat16_rn(v);
-    d[(int64_t)p * j.plane_stride] = q;
-    v -= __bfloat162float(q);
+  for (int i = 0; i < 4; ++i) {
+    const int a = ty + i * 8;
+    const int r = by_rows ? r0 + tx : r0 + a, c = by_rows ? c0 + a : c0 + tx;
+    float v = 0.f;
+    if (r < j.rows && c < j.cols) v = j.src[(int64_t)r * j.ld_r + (int64_t)c * j.ld_c];
+    if (by_rows) tile[tx][a] = v; else tile[a][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    if (r < j.rows && c < j.cols) {
+      float v = tile[ty + i * 8][tx];
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(j.dst) + (int64_t)r * j.ld_out + c;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const __nv_bfloat16 q = __float2bfloat16_rn(v);
+        d[(int64_t)p * j.plane_stride] = q;
+        v -= __bfloat162float(q);
+      }
+    }
   }
 }
 

@@ -219,11 +219,13 @@ __global__ void __launch_bounds__(128) rows_gather_dropout_bp_kernel(const float
                                                                      uint32_t thr, float scale, uint32_t seed,
                                                                      const uint32_t* __restrict__ salt,
                                                                      __nv_bfloat16* __restrict__ out, int64_t ld_out,
-                                                                     int64_t plane_stride, int nplanes) {
+                                                                     int64_t plane_stride, int nplanes, int src_rows) {
   const uint32_t sd = seed + (thr ? __ldg(salt) : 0u);
   const int wq = ((W + 7) & ~7) >> 2;
   for (int r = blockIdx.x; r < R; r += gridDim.x) {
-    const float* s = src + (idx ? idx[r] : (int64_t)r) * ld_src;
+    const int64_t sr = idx ? idx[r] : (int64_t)r;
+    if (src_rows > 0 && (sr < 0 || sr >= src_rows)) __trap();   // out-of-vocabulary id: fail like nn.Embedding's device assert
+    const float* s = src + sr * ld_src;
     __nv_bfloat16* d = out + (int64_t)r * ld_out;
     for (int q = threadIdx.x; q < wq; q += blockDim.x) {
       float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -234,6 +236,89 @@ __global__ void __launch_bounds__(128) rows_gather_dropout_bp_kernel(const float
       }
       planes_store4(d + q * 4, plane_stride, nplanes, v);
     }
+  }
+}
+
+// ---- segment index arithmetic (reference basic_fc_model.py:80-121: the per-claim Python loops) in ONE launch -------------
+// evd_cnt (B,) -> offsets (B+1,) = exclusive prefix sums, seg_of_row (B1,) = claim of every flattened evidence,
+// slot_of_row (B1,) = claim * n + position inside the claim. Single block; B1 is the host-known row count.
+__global__ void __launch_bounds__(1024) segments_kernel(const int64_t* __restrict__ cnt64, const int32_t* __restrict__ cnt32,
+                                                        int B, int B1, int n, int32_t* __restrict__ seg,
+                                                        int32_t* __restrict__ slot, int32_t* __restrict__ offsets) {
+  extern __shared__ int s_off[];                      // B + 1
+  for (int c = threadIdx.x; c <= B; c += blockDim.x) {
+    int acc = 0;
+    for (int q = 0; q < c; ++q) acc += cnt64 ? (int)cnt64[q] : cnt32[q];
+    s_off[c] = acc;
+    offsets[c] = acc;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < B1; r += blockDim.x) {
+    int lo = 0, hi = B - 1;                           // last claim whose offset is <= r
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    seg[r] = lo;
+    slot[r] = lo * n + (r - s_off[lo]);
+  }
+}
+
+// mask[i] = ids[i] >= 1 (word level, gbss.py:98) / mask[r] = sum_j ids[r, j] >= 1 (evidence level, gbss.py:215)
+__global__ void __launch_bounds__(256) ids_mask_kernel(const int64_t* __restrict__ ids64, const int32_t* __restrict__ ids32,
+                                                       int64_t rows, int W, uint8_t* __restrict__ mask) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  long long acc = 0;
+  for (int j = lane; j < W; j += 32) acc += ids64 ? (long long)ids64[r * W + j] : (long long)ids32[r * W + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) mask[r] = acc >= 1 ? 1 : 0;
+}
+
+// ---- trainable source embeddings (reference base_model.py:184-188, gbss.py:157-171): out[r,:] = table[max(idx[r],0),:]
+// (the -1 padding id is looked up as row 0, gbss.py:166-168) and its dense, DETERMINISTIC gradient: one block per table
+// row sums the matching output-gradient rows in index order.
+__global__ void __launch_bounds__(128) embedding_rows_fwd_kernel(const float* __restrict__ table, int E, const int64_t* __restrict__ idx,
+                                                                 int R, float* __restrict__ out, int64_t ld_out) {
+  const int r = blockIdx.x;
+  int64_t v = idx[r];
+  if (v < 0) v = 0;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) out[(int64_t)r * ld_out + c] = __ldg(table + v * E + c);
+}
+__global__ void __launch_bounds__(128) embedding_rows_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const int64_t* __restrict__ idx,
+                                                                 int R, int E, float* __restrict__ dtable, int accumulate) {
+  extern __shared__ int s_rows[];                     // rows of g that hit this table row (compacted, in order)
+  __shared__ int s_n;
+  const int v = blockIdx.x;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  // ordered compaction: chunks of blockDim rows, ballot-free (R is a few hundred to a few thousand)
+  for (int r0 = 0; r0 < R; r0 += blockDim.x) {
+    const int r = r0 + threadIdx.x;
+    int64_t id = r < R ? idx[r] : -2;
+    if (id == -1) id = 0;
+    const bool hit = id == v;
+    // in-order positions through a block-wide prefix count (warp ballots + per-warp offsets)
+    __shared__ int s_w[4];
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) s_w[warp] = __popc(b);
+    __syncthreads();
+    int base = s_n;
+    for (int w = 0; w < warp; ++w) base += s_w[w];
+    if (hit) s_rows[base + __popc(b & ((1u << lane) - 1u))] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) s_n += s_w[0] + s_w[1] + s_w[2] + s_w[3];
+    __syncthreads();
+  }
+  const int n = s_n;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float acc = 0.f;
+    for (int e = 0; e < n; ++e) acc += g[(int64_t)s_rows[e] * ld_g + c];
+    float* d = dtable + (int64_t)v * E + c;
+    *d = accumulate ? *d + acc : acc;
   }
 }
 
@@ -410,7 +495,7 @@ extern "C" int get_ggnn_gate_bwd_bp(const float* dout, const float* z, const flo
   return 0;
 }
 
-extern "C" int get_rows_gather_dropout_bp(const float* src, int64_t ld_src, const int64_t* idx, int R, int W, float p,
+extern "C" int get_rows_gather_dropout_bp(const float* src, int64_t ld_src, int src_rows, const int64_t* idx, int R, int W, float p,
                                           uint32_t seed, void* planes, int64_t ld_out, int64_t plane_stride, int nplanes,
                                           void* stream) {
   GETB_REQUIRE(src && planes && p >= 0.f && p < 1.f, "get_rows_gather_dropout_bp: bad arguments");
@@ -422,8 +507,54 @@ extern "C" int get_rows_gather_dropout_bp(const float* src, int64_t ld_src, cons
   rows_gather_dropout_bp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, ld_src, idx, R, W, p > 0.f ? drop_threshold(p) : 0u,
                                                                        1.0f / (1.0f - p), seed, dropout_salt_ptr(),
                                                                        reinterpret_cast<__nv_bfloat16*>(planes), ld_out,
-                                                                       plane_stride, nplanes);
+                                                                       plane_stride, nplanes, src_rows);
   GETB_CHECK_LAUNCH("get_rows_gather_dropout_bp");
+  return 0;
+}
+
+extern "C" int get_segments_i32(const void* evd_cnt, int cnt_is_int64, int B, int B1, int n, int32_t* seg_of_row,
+                                int32_t* slot_of_row, int32_t* offsets, void* stream) {
+  GETB_REQUIRE(evd_cnt && seg_of_row && slot_of_row && offsets && B >= 1 && B1 >= 0 && n >= 1, "get_segments_i32: bad arguments");
+  GETB_REQUIRE(B <= 8192, "get_segments_i32: at most 8192 claims per call");
+  segments_kernel<<<1, 1024, (size_t)(B + 1) * sizeof(int), (cudaStream_t)stream>>>(
+      cnt_is_int64 ? reinterpret_cast<const int64_t*>(evd_cnt) : nullptr, cnt_is_int64 ? nullptr : reinterpret_cast<const int32_t*>(evd_cnt),
+      B, B1, n, seg_of_row, slot_of_row, offsets);
+  GETB_CHECK_LAUNCH("get_segments_i32");
+  return 0;
+}
+
+extern "C" int get_ids_mask_u8(const void* ids, int ids_is_int64, int64_t rows, int W, uint8_t* mask, void* stream) {
+  GETB_REQUIRE(ids && mask && rows >= 0 && W >= 1, "get_ids_mask_u8: bad arguments");
+  if (rows == 0) return 0;
+  ids_mask_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+      ids_is_int64 ? reinterpret_cast<const int64_t*>(ids) : nullptr, ids_is_int64 ? nullptr : reinterpret_cast<const int32_t*>(ids), rows, W, mask);
+  GETB_CHECK_LAUNCH("get_ids_mask_u8");
+  return 0;
+}
+
+extern "C" int get_embedding_rows_fwd_f32(const float* table, int V, int E, const int64_t* idx, int R, float* out, int64_t ld_out,
+                                          void* stream) {
+  GETB_REQUIRE(table && idx && out && V >= 1 && E >= 1 && ld_out >= E, "get_embedding_rows_fwd_f32: bad arguments");
+  if (R <= 0) return 0;
+  embedding_rows_fwd_kernel<<<R, 128, 0, (cudaStream_t)stream>>>(table, E, idx, R, out, ld_out);
+  GETB_CHECK_LAUNCH("get_embedding_rows_fwd_f32");
+  return 0;
+}
+
+extern "C" int get_embedding_rows_bwd_f32(const float* g, int64_t ld_g, const int64_t* idx, int R, int V, int E, float* dtable,
+                                          int accumulate, void* stream) {
+  GETB_REQUIRE(g && idx && dtable && V >= 1 && E >= 1 && R >= 0 && ld_g >= E, "get_embedding_rows_bwd_f32: bad arguments");
+  GETB_REQUIRE((size_t)R * sizeof(int) <= 160 * 1024, "get_embedding_rows_bwd_f32: at most 40960 looked-up rows per call");
+  const size_t smem = (size_t)(R > 0 ? R : 1) * sizeof(int);
+  if (smem > 48 * 1024) {
+    static bool done = false;
+    if (!done) {
+      cudaFuncSetAttribute(embedding_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      done = true;
+    }
+  }
+  embedding_rows_bwd_kernel<<<V, 128, smem, (cudaStream_t)stream>>>(g, ld_g, idx, R, E, dtable, accumulate);
+  GETB_CHECK_LAUNCH("get_embedding_rows_bwd_f32");
   return 0;
 }
 

@@ -98,19 +98,6 @@ class Graph_basedSemantiStructure(nn.Module):
         self._side_stream = None
 
     # ------------------------------------------------------------------------------------------
-    @staticmethod
-    def _segments(evd_cnt: torch.Tensor, b1: int, n: int):
-        """Device-side index arithmetic replacing the per-claim loops of basic_fc_model.py:80-121.
-        Returns seg_of_row (B1,), slot_of_row (B1,) = claim*n + j, offsets (B+1,), all int32. No host sync:
-        B1 is known from the shape of the flattened evidence tensor."""
-        cnt = evd_cnt.to(torch.int64)
-        B = cnt.shape[0]
-        offsets = torch.zeros((B + 1,), dtype=torch.int64, device=cnt.device)
-        offsets[1:] = torch.cumsum(cnt, 0)
-        seg = torch.repeat_interleave(torch.arange(B, device=cnt.device), cnt, output_size=b1)
-        slot = seg * n + (torch.arange(b1, device=cnt.device) - offsets[seg])
-        return seg.to(torch.int32), slot.to(torch.int32), offsets.to(torch.int32)
-
     def forward(self, query: torch.Tensor, document: torch.Tensor, verbose=False, **kargs):
         K = KeyWordSettings
         assert K.Query_lens in kargs and K.Doc_lens in kargs
@@ -126,7 +113,7 @@ class Graph_basedSemantiStructure(nn.Module):
         evd_cnt = kargs[K.EvidenceCountPerQuery]
         assert evd_cnt.size(0) == batch_size
         seeds = self.dropout_seeds or {}
-        seg, slot, offsets = self._segments(evd_cnt, b1, n)
+        seg, slot, offsets = ops.segments(evd_cnt, b1, n)       # replaces the per-claim loops of bfm.py:80-121
         emb_fused = not self.embedding.weight.requires_grad
 
         # claim graph -> masked mean (gbss.py:144-155). The claim branch is a chain of small kernels (B*30 rows, a few
@@ -165,22 +152,20 @@ class Graph_basedSemantiStructure(nn.Module):
         query_repr = ops.SegmentExpandFn.apply(q_claim, seg, offsets)                # (B1, H)
 
         # word-level attention (gbss.py:110, 173-193)
-        avg, word_att = self.self_att_word(query_repr, doc_out, doc >= 1, right_planes=doc_planes)
+        avg, word_att = self.self_att_word(query_repr, doc_out, ops.ids_mask(doc), right_planes=doc_planes)    # doc >= 1
         avg = torch.flatten(avg, start_dim=1)                                        # (B1, H*heads), index d*heads+head
 
         # evidence-level attention (gbss.py:113-119, 195-221)
         if self.use_claim_source:
-            claim_embs = self.claim_source_embs(kargs[K.QuerySources].long()).squeeze(1)   # (B, E_c)
+            claim_embs = ops.embedding_rows(self.claim_source_embs.weight, kargs[K.QuerySources])         # (B, E_c)
             new_left = torch.cat([claim_embs, q_claim], dim=-1)      # == _pad_right(_pad_left(.))[:, 0, :]
         else:
             new_left = q_claim
         extra = None
         if self.use_article_source:
-            src = kargs[K.DocSources]
-            src = src.masked_fill(src == -1, 0)
-            extra = self.article_source_embs(src.long()).reshape(batch_size * n, -1)
+            extra = ops.embedding_rows(self.article_source_embs.weight, kargs[K.DocSources])   # -1 -> row 0 (gbss.py:166-168)
         padded = ops.SegmentPadFn.apply(avg, slot, batch_size * n, extra).view(batch_size, n, -1)
-        evd_mask = torch.sum(document, dim=-1) >= 1
+        evd_mask = ops.ids_mask(document, reduce_last=True)                          # sum(document, -1) >= 1
         att_avg, evd_att = self.self_att_evd(new_left, padded, evd_mask)
         final = torch.cat([new_left, torch.flatten(att_avg, start_dim=1)], dim=-1)   # gbss.py:264-267
         hid = ops.linear(final, self.out[0].weight, self.out[0].bias)                # gbss.py:121

@@ -174,10 +174,80 @@ def rows_gather_dropout_planes(src: torch.Tensor, idx: Optional[torch.Tensor], r
     out = alloc_planes(nplanes, rows, W, src.device)
     if idx is not None:
         assert idx.dtype == torch.int64 and idx.is_cuda and idx.is_contiguous() and idx.numel() == rows
-    _lib.check(lib.get_rows_gather_dropout_bp(src.data_ptr(), src.stride(0), _ptr(idx), rows, W, float(p), seed & 0xFFFFFFFF,
-                                              out.ptr, out.ld, out.plane_stride, nplanes, _stream()),
-               "get_rows_gather_dropout_bp")
+    _lib.check(lib.get_rows_gather_dropout_bp(src.data_ptr(), src.stride(0), src.shape[0] if idx is not None else 0, _ptr(idx),
+                                              rows, W, float(p), seed & 0xFFFFFFFF, out.ptr, out.ld, out.plane_stride, nplanes,
+                                              _stream()), "get_rows_gather_dropout_bp")
     return out
+
+
+def segments(evd_cnt: torch.Tensor, b1: int, n: int):
+    """seg_of_row (B1,), slot_of_row (B1,) = claim*n + j, offsets (B+1,) (all int32) from the per-claim evidence counts in one
+    launch: the index arithmetic that replaces the per-claim loops of basic_fc_model.py:80-121. No host sync (B1 is the
+    shape of the flattened evidence tensor)."""
+    lib = _lib.load()
+    if not evd_cnt.is_cuda:
+        raise RuntimeError("get_b200: evd_cnt must be a CUDA tensor (there is no CPU path)")
+    if evd_cnt.dtype not in (torch.int64, torch.int32):
+        evd_cnt = evd_cnt.to(torch.int64)
+    evd_cnt = evd_cnt.contiguous()
+    B = evd_cnt.shape[0]
+    dev = evd_cnt.device
+    seg = torch.empty((b1,), dtype=torch.int32, device=dev)
+    slot = torch.empty((b1,), dtype=torch.int32, device=dev)
+    off = torch.empty((B + 1,), dtype=torch.int32, device=dev)
+    _lib.check(lib.get_segments_i32(evd_cnt.data_ptr(), int(evd_cnt.dtype == torch.int64), B, int(b1), int(n), seg.data_ptr(),
+                                    slot.data_ptr(), off.data_ptr(), _stream()), "get_segments_i32")
+    return seg, slot, off
+
+
+def ids_mask(ids: torch.Tensor, reduce_last: bool = False) -> torch.Tensor:
+    """uint8 attention mask from token ids: `ids >= 1` element-wise (gbss.py:98), or with reduce_last
+    `sum(ids, -1) >= 1` (gbss.py:215)."""
+    lib = _lib.load()
+    if not ids.is_cuda:
+        raise RuntimeError("get_b200: ids must be a CUDA tensor (there is no CPU path)")
+    if ids.dtype not in (torch.int64, torch.int32):
+        ids = ids.to(torch.int64)
+    ids = ids.contiguous()
+    W = ids.shape[-1] if reduce_last else 1
+    shape = ids.shape[:-1] if reduce_last else ids.shape
+    out = torch.empty(shape, dtype=torch.uint8, device=ids.device)
+    _lib.check(lib.get_ids_mask_u8(ids.data_ptr(), int(ids.dtype == torch.int64), out.numel(), W, out.data_ptr(), _stream()),
+               "get_ids_mask_u8")
+    return out
+
+
+class EmbeddingRowsFn(torch.autograd.Function):
+    """Trainable source embeddings (base_model.py:184-188; the -1 padding id reads row 0, gbss.py:166-168) written into a
+    column block of `out` when given; dense deterministic table gradient."""
+
+    @staticmethod
+    def forward(ctx, table, idx):
+        lib = _lib.load()
+        _chk_f32(table, "table")
+        table = table.contiguous()
+        idx = idx.reshape(-1).to(torch.int64).contiguous()
+        R, (V, E) = idx.shape[0], table.shape
+        out = torch.empty((R, E), dtype=torch.float32, device=table.device)
+        _lib.check(lib.get_embedding_rows_fwd_f32(table.data_ptr(), V, E, idx.data_ptr(), R, out.data_ptr(), E, _stream()),
+                   "get_embedding_rows_fwd_f32")
+        ctx.save_for_backward(idx, table)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        idx, table = ctx.saved_tensors
+        V, E = table.shape
+        g = g if (g.dim() == 2 and g.stride(1) == 1) else g.contiguous()
+        dst, acc, ret = _grad_target(table)
+        _lib.check(lib.get_embedding_rows_bwd_f32(g.data_ptr(), g.stride(0), idx.data_ptr(), idx.shape[0], V, E, dst.data_ptr(),
+                                                  int(acc), _stream()), "get_embedding_rows_bwd_f32")
+        return ret, None
+
+
+def embedding_rows(table, idx):
+    return EmbeddingRowsFn.apply(table, idx)
 
 
 def new_seed() -> int:
@@ -745,18 +815,26 @@ class ConcatAttFn(torch.autograd.Function):
         if d_att is not None:
             d_att = d_att.contiguous()
         de = torch.empty((G * P, Cn), **f32)
-        du = torch.empty((G * P, H), **f32)
         du_sum = torch.empty((G, H), **f32)
         dright = torch.empty((G * P, Dr), **f32)
-        _lib.check(lib.get_att_pool_bwd_f32(t.data_ptr(), right2d.data_ptr(), _ld(right2d), W2.data_ptr(),
-                                            att.data_ptr(), d_pooled.data_ptr(), Dr * Cn, _ptr(d_att),
-                                            G, P, H, Dr, Cn, de.data_ptr(), du.data_ptr(), du_sum.data_ptr(),
-                                            dright.data_ptr(), Dr, 0, _stream()), "get_att_pool_bwd_f32")
+        use_tc = rP_t is not None
+        du = duP = None
+        if use_tc:
+            # du leaves the kernel as bf16 planes: it is only ever the operand of the two contractions below
+            duP = alloc_planes(gemm_mode(False), G * P, H, dev)
+            _lib.check(lib.get_att_pool_bwd_bp(t.data_ptr(), right2d.data_ptr(), _ld(right2d), W2.data_ptr(), att.data_ptr(),
+                                               d_pooled.data_ptr(), Dr * Cn, _ptr(d_att), G, P, H, Dr, Cn, de.data_ptr(),
+                                               duP.ptr, duP.ld, duP.plane_stride, duP.nplanes, du_sum.data_ptr(),
+                                               dright.data_ptr(), Dr, 0, _stream()), "get_att_pool_bwd_bp")
+        else:
+            du = torch.empty((G * P, H), **f32)
+            _lib.check(lib.get_att_pool_bwd_f32(t.data_ptr(), right2d.data_ptr(), _ld(right2d), W2.data_ptr(),
+                                                att.data_ptr(), d_pooled.data_ptr(), Dr * Cn, _ptr(d_att),
+                                                G, P, H, Dr, Cn, de.data_ptr(), du.data_ptr(), du_sum.data_ptr(),
+                                                dright.data_ptr(), Dr, 0, _stream()), "get_att_pool_bwd_f32")
         need = ctx.needs_input_grad
         dleft = dW1 = dW2 = None
         W1R = W1[:, X:]
-        use_tc = rP_t is not None
-        duP = to_planes(du, gemm_mode(False)) if use_tc and (need[1] or need[3]) else None
         if need[1]:
             gemm([(duP if duP is not None else du, W1R.t())], dright, accumulate=True, tc=True)
         if need[4]:
@@ -783,7 +861,7 @@ class ConcatAttFn(torch.autograd.Function):
 
 
 def concat_att(left, right, mask, W1, W2, right_planes=None):
-    mask_u8 = (mask != 0).to(torch.uint8)
+    mask_u8 = mask if mask.dtype == torch.uint8 else (mask != 0).to(torch.uint8)
     return ConcatAttFn.apply(left, right, mask_u8, W1, W2, right_planes)
 
 

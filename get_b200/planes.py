@@ -119,7 +119,7 @@ class WeightPack(object):
             j.rows, j.cols = w.shape
             j.dst = P.t.data_ptr() + 2 * (r0 * P.ld + c0)
             j.ld_out, j.plane_stride, j.first_block, j.kind = P.ld, P.plane_stride, blk, 0
-            blk += (w.shape[0] * w.shape[1] + 255) // 256
+            blk += ((w.shape[0] + 31) // 32) * ((w.shape[1] + 31) // 32)
             out.append(j)
         for (b0, b1, off) in self.bias_blocks:
             j = _lib.PackJob()
@@ -127,7 +127,7 @@ class WeightPack(object):
             j.ld_r, j.ld_c, j.rows, j.cols = 1, 1, b0.numel(), 1
             j.dst = self.bias.data_ptr() + 4 * off
             j.ld_out, j.plane_stride, j.first_block, j.kind = 0, 0, blk, 1
-            blk += (b0.numel() + 255) // 256
+            blk += (b0.numel() + 1023) // 1024
             out.append(j)
         return out, blk
 

@@ -194,7 +194,8 @@ int get_to_planes_bf16(const float* src, int64_t ld_src, int rows, int cols, voi
  * ld_out, plane pitch plane_stride; dst already points at the block's first element, so several matrices can be packed
  * side by side / stacked into one plane tensor whose padding was zeroed once). kind 1: fp32 vector
  * dst[i] = src[i] + (src2 ? src2[i] : 0), i < rows (fused bias vectors). Job j covers blocks
- * [first_block, first_block + ceil(rows*max(cols,1)/256)) of the launch. */
+ * [first_block, first_block + nblocks) of the launch, nblocks = ceil(rows/32)*ceil(cols/32) (kind 0: one block per
+ * 32 x 32 tile) or ceil(rows/1024) (kind 1). */
 typedef struct get_pack_job {
   const float* src; const float* src2;
   int64_t ld_r, ld_c;
@@ -263,6 +264,14 @@ int get_att_pool_bwd_f32(const float* t, const float* right, int64_t ld_right, c
                          float* de, float* du, float* du_sum, float* dright, int64_t ld_dright,
                          int accumulate, void* stream);
 
+/* The same backward with du written as bf16 planes [nplanes][G*P][ld_dup] (operand of the tensor-core contractions
+ * dright += du @ W1_right and dW1_right = du^T @ right, see get_gemm_bp) instead of fp32. */
+int get_att_pool_bwd_bp(const float* t, const float* right, int64_t ld_right, const float* W2,
+                        const float* att, const float* d_pooled, int64_t ld_dpooled, const float* d_att,
+                        int G, int P, int H, int Dr, int C, float* de, void* du_planes, int64_t ld_dup,
+                        int64_t plane_stride, int nplanes, float* du_sum, float* dright, int64_t ld_dright,
+                        int accumulate, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GGNN backward, element-wise stage: from dout, z, h, x  (all (M,H) contiguous)
  *   dhp = dout*z*(1-h^2) ; dzp = dout*(h-x)*z*(1-z) ; dx = dout*(1-z).
@@ -292,6 +301,25 @@ int get_rows_scatter_f32(const float* src, int64_t ld_src, const int32_t* idx, i
 int get_segment_sum_f32(const float* src, int64_t ld_src, const int32_t* offsets, int S, int W,
                         float* out, int64_t ld_out, void* stream);
 
+/* The index vectors above from the per-claim evidence counts, in one launch (replaces the per-claim Python loops and
+ * host syncs of bfm.py:86-90,113-118): offsets (B+1,) = exclusive prefix sums of evd_cnt (int64 or int32, B <= 8192),
+ * seg_of_row / slot_of_row (B1,) with B1 = sum(evd_cnt) known on the host (shape of the flattened evidence tensor). */
+int get_segments_i32(const void* evd_cnt, int cnt_is_int64, int B, int B1, int n, int32_t* seg_of_row,
+                     int32_t* slot_of_row, int32_t* offsets, void* stream);
+
+/* Attention masks from token ids (int64 or int32), one warp per row: mask[r] = (sum_j ids[r*W + j] >= 1).
+ * W = 1 gives the word-level mask `doc >= 1` (gbss.py:98; ids are never negative), W = R the evidence-level mask
+ * `sum(document, -1) >= 1` (gbss.py:215). */
+int get_ids_mask_u8(const void* ids, int ids_is_int64, int64_t rows, int W, uint8_t* mask, void* stream);
+
+/* Trainable source embeddings (base_model.py:184-188): out[r,:] = table[max(idx[r], 0), :] (the -1 padding id is looked
+ * up as row 0, gbss.py:166-168); backward = the dense (V,E) table gradient, summed in index order by one block per
+ * table row (deterministic; no atomics). */
+int get_embedding_rows_fwd_f32(const float* table, int V, int E, const int64_t* idx, int R, float* out, int64_t ld_out,
+                               void* stream);
+int get_embedding_rows_bwd_f32(const float* g, int64_t ld_g, const int64_t* idx, int R, int V, int E, float* dtable,
+                               int accumulate, void* stream);
+
 /* Masked mean over the nodes of each claim graph (gbss.py:145-153):
  * out[g,:] = sum_i [ids[g,i] > 0] * h[g,i,:] / lens[g];  and its backward dh[g,i,:] = [ids>0]*dout[g,:]/lens[g]. */
 int get_masked_mean_fwd_f32(const float* h, const int64_t* ids, const int64_t* lens, int G, int N, int H,
@@ -308,10 +336,12 @@ int get_rows_gather_dropout_f32(const float* src, int64_t ld_src, const int64_t*
 /* Plane-emitting variants for the bf16-plane contraction (get_gemm_bp): the same computations with the result written
  * as bf16 planes [nplanes][rows][ld] (pad columns up to the next multiple of 8 written as zeros).
  * get_ggnn_gate_bwd_bp: dz' -> column block `col_z`, dh' -> column block `col_h` of the gate-gradient plane buffer
- * [dz' | dr' | dh'] with row pitch ld_g; dx stays fp32 (M,H). */
+ * [dz' | dr' | dh'] with row pitch ld_g; dx stays fp32 (M,H).
+ * get_rows_gather_dropout_bp: src_rows > 0 bounds-checks the gathered row ids (an id outside [0, src_rows) traps the
+ * kernel, like the device assert of the reference's nn.Embedding). */
 int get_ggnn_gate_bwd_bp(const float* dout, const float* z, const float* h, const float* x, int M, int H, void* dg,
                          int64_t ld_g, int64_t plane_stride, int nplanes, int col_z, int col_h, float* dx, void* stream);
-int get_rows_gather_dropout_bp(const float* src, int64_t ld_src, const int64_t* idx, int R, int W, float p,
+int get_rows_gather_dropout_bp(const float* src, int64_t ld_src, int src_rows, const int64_t* idx, int R, int W, float p,
                                uint32_t seed, void* planes, int64_t ld_out, int64_t plane_stride, int nplanes,
                                void* stream);
 
