@@ -109,6 +109,7 @@ SIGNATURES = {
     "get_dropout_salt_set": (_I, [_U, _P]),
     "get_dropout_salt_advance": (_I, [_P]),
     "get_dropout_salt_get": (_I, [C.POINTER(C.c_uint32)]),
+    "get_adam_flat_f32": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P, _P]),
     "get_build_word_graphs": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "get_cross_entropy_f32": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "get_b200_abi_version": (_I, []),

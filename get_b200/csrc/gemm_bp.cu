@@ -769,7 +769,9 @@ static int bp_plan(const get_gemm_bp_desc* d, BpCfg& cfg, BpParams& p) {
     cfg.kblocks_total += cfg.kblocks[s];
   }
   p.M = d->M; p.N = d->N;
-  p.Npad = d->planes_out ? bp_round_up(d->N, 8) : d->N;
+  // columns written to planes_out: the logical ones plus padding up to a multiple of 8 (zeros; with pad_one column N holds
+  // 1.0, so the extent always contains it)
+  p.Npad = d->planes_out ? bp_round_up(d->N + (d->planes_out_pad_one ? 1 : 0), 8) : d->N;
   p.epilogue = d->epilogue; p.accumulate = d->accumulate;
   p.C = d->C; p.ldc = d->ldc; p.out1 = d->out1; p.ld_out1 = d->ld_out1;
   p.has_c = d->C != nullptr; p.has_o1 = d->out1 != nullptr; p.has_pl = d->planes_out != nullptr;

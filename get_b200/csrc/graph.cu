@@ -230,9 +230,12 @@ __global__ void __launch_bounds__(GRAPH_THREADS) graph_kernel(const __grid_const
           }
         }
       }
-      if (prow && (H & 7) && lane == 0) {
-        const float vv[4] = {p.pad_one ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
-        planes_store4(prow + H, p.ps_p, p.np_p, vv);
+      if (prow) {   // padding quads up to a multiple of 8 columns (room for the ones column when pad_one)
+        const int npq = ((((H + (p.pad_one ? 1 : 0)) + 7) & ~7) - H) >> 2;
+        if (lane < npq) {
+          const float vv[4] = {(p.pad_one && lane == 0) ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
+          planes_store4(prow + H + lane * 4, p.ps_p, p.np_p, vv);
+        }
       }
     } else {
 #pragma unroll
@@ -503,9 +506,12 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
         }
       }
     }
-    if (prow && (H & 7) && lane == 0) {
-      const float vv[4] = {p.pad_one ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
-      planes_store4(prow + H, p.ps_p, p.np_p, vv);
+    if (prow) {   // padding quads up to a multiple of 8 columns (room for the ones column when pad_one)
+      const int npq = ((((H + (p.pad_one ? 1 : 0)) + 7) & ~7) - H) >> 2;
+      if (lane < npq) {
+        const float vv[4] = {(p.pad_one && lane == 0) ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
+        planes_store4(prow + H + lane * 4, p.ps_p, p.np_p, vv);
+      }
     }
   }
 }
@@ -837,7 +843,7 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
   GETB_REQUIRE(!p.accumulate || p.out, "%s: accumulate needs the fp32 output", name);
   if (p.out_p)
     GETB_REQUIRE((p.H % 4) == 0 && aligned16(p.x) && (!p.out || aligned16(p.out)) && (((uintptr_t)p.out_p) & 7u) == 0 &&
-                     (p.ld_p % 4) == 0 && (p.ps_p % 4) == 0 && p.np_p >= 1 && p.np_p <= 3 && p.ld_p >= ((p.H + 7) & ~7),
+                     (p.ld_p % 4) == 0 && (p.ps_p % 4) == 0 && p.np_p >= 1 && p.np_p <= 3 && p.ld_p >= ((p.H + (p.pad_one ? 1 : 0) + 7) & ~7),
                  "%s: plane output needs H %% 4 == 0 and aligned tensors", name);
   if (p.G == 0) return 0;
   {

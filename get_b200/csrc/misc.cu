@@ -289,36 +289,59 @@ __global__ void __launch_bounds__(128) embedding_rows_fwd_kernel(const float* __
 }
 __global__ void __launch_bounds__(128) embedding_rows_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const int64_t* __restrict__ idx,
                                                                  int R, int E, float* __restrict__ dtable, int accumulate) {
-  extern __shared__ int s_rows[];                     // rows of g that hit this table row (compacted, in order)
-  __shared__ int s_n;
+  // block = one table row; thread = one column; the looked-up rows are visited in index order (deterministic sum)
+  extern __shared__ int s_idx[];                      // the R looked-up ids (-1 -> 0)
   const int v = blockIdx.x;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  // ordered compaction: chunks of blockDim rows, ballot-free (R is a few hundred to a few thousand)
-  for (int r0 = 0; r0 < R; r0 += blockDim.x) {
-    const int r = r0 + threadIdx.x;
-    int64_t id = r < R ? idx[r] : -2;
-    if (id == -1) id = 0;
-    const bool hit = id == v;
-    // in-order positions through a block-wide prefix count (warp ballots + per-warp offsets)
-    __shared__ int s_w[4];
-    const unsigned b = __ballot_sync(0xffffffffu, hit);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) s_w[warp] = __popc(b);
-    __syncthreads();
-    int base = s_n;
-    for (int w = 0; w < warp; ++w) base += s_w[w];
-    if (hit) s_rows[base + __popc(b & ((1u << lane) - 1u))] = r;
-    __syncthreads();
-    if (threadIdx.x == 0) s_n += s_w[0] + s_w[1] + s_w[2] + s_w[3];
-    __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const int64_t id = idx[r];
+    s_idx[r] = id < 0 ? 0 : (int)id;
   }
-  const int n = s_n;
+  __syncthreads();
   for (int c = threadIdx.x; c < E; c += blockDim.x) {
     float acc = 0.f;
-    for (int e = 0; e < n; ++e) acc += g[(int64_t)s_rows[e] * ld_g + c];
+    for (int r = 0; r < R; ++r)
+      if (s_idx[r] == v) acc += g[(int64_t)r * ld_g + c];
     float* d = dtable + (int64_t)v * E + c;
     *d = accumulate ? *d + acc : acc;
+  }
+}
+
+// ---- Adam with L2 weight decay over flat buffers (the reference fitter's torch.optim.Adam(lr, weight_decay),
+// Fitting/FittingFC/declare_fitter.py:57-61): g += wd*p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). The step counter t lives on the device (CUDA-graph replays).
+__global__ void adam_step_advance_kernel(float* step) { *step += 1.0f; }
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n4, int64_t n, float lr, float b1, float b2,
+                                                        float eps, float wd, const float* __restrict__ step) {
+  const float t = __ldg(step);
+  const float bc1 = 1.0f - powf(b1, t), bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    float pp[4], gg[4], mm[4], vv[4];
+    const int64_t i = q * 4;
+    const int nv = (int)min((int64_t)4, n - i);
+    if (nv == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(p + i), b = *reinterpret_cast<const float4*>(g + i);
+      const float4 c = *reinterpret_cast<const float4*>(m + i), d = *reinterpret_cast<const float4*>(v + i);
+      pp[0] = a.x; pp[1] = a.y; pp[2] = a.z; pp[3] = a.w; gg[0] = b.x; gg[1] = b.y; gg[2] = b.z; gg[3] = b.w;
+      mm[0] = c.x; mm[1] = c.y; mm[2] = c.z; mm[3] = c.w; vv[0] = d.x; vv[1] = d.y; vv[2] = d.z; vv[3] = d.w;
+    } else {
+      for (int e = 0; e < 4; ++e) { const bool ok = e < nv; pp[e] = ok ? p[i + e] : 0.f; gg[e] = ok ? g[i + e] : 0.f; mm[e] = ok ? m[i + e] : 0.f; vv[e] = ok ? v[i + e] : 0.f; }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = gg[e] + wd * pp[e];
+      mm[e] = b1 * mm[e] + (1.0f - b1) * gr;
+      vv[e] = b2 * vv[e] + (1.0f - b2) * gr * gr;
+      pp[e] -= step_size * mm[e] / (sqrtf(vv[e]) / bc2_sqrt + eps);
+    }
+    if (nv == 4) {
+      *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+      for (int e = 0; e < nv; ++e) { p[i + e] = pp[e]; m[i + e] = mm[e]; v[i + e] = vv[e]; }
+    }
   }
 }
 
@@ -555,6 +578,21 @@ extern "C" int get_embedding_rows_bwd_f32(const float* g, int64_t ld_g, const in
   }
   embedding_rows_bwd_kernel<<<V, 128, smem, (cudaStream_t)stream>>>(g, ld_g, idx, R, E, dtable, accumulate);
   GETB_CHECK_LAUNCH("get_embedding_rows_bwd_f32");
+  return 0;
+}
+
+extern "C" int get_adam_flat_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, float* step, void* stream) {
+  GETB_REQUIRE(param && grad && exp_avg && exp_avg_sq && step && n >= 0, "get_adam_flat_f32: bad arguments");
+  GETB_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), "get_adam_flat_f32: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  adam_step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  GETB_CHECK_LAUNCH("get_adam_flat_f32/step");
+  const int64_t n4 = (n + 3) / 4;
+  int grid = ceil_div(n4, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, lr, beta1, beta2, eps, weight_decay, step);
+  GETB_CHECK_LAUNCH("get_adam_flat_f32");
   return 0;
 }
 

@@ -145,6 +145,7 @@ class Graph_basedSemantiStructure(nn.Module):
         else:
             doc_out = self.ggnn_with_gsl(doc_adj, self.embedding(doc.long()), seeds=blk_seeds, out_planes=npl)
         doc_planes = self.ggnn_with_gsl.last_out_planes
+        doc_out = ops.grad_marker(doc_out, "head")   # backward: attention / MLP / source-embedding gradients are complete here
 
         if fork:
             cur.wait_stream(self._side_stream)

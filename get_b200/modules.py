@@ -125,6 +125,7 @@ class GGNN_with_GSL(nn.Module):
         if seeds is None:
             seeds = tuple(ops.new_seed() for _ in range(3)) if self.training else (0, 0, 0)
         f1 = self.feat_prop1(adj, feat, table=table, ids=ids, seed=seeds[0], exact_fwd=True)   # decides the kept node set
+        f1 = ops.grad_marker(f1, "feat_prop2")      # backward: feat_prop2's gradients are complete when dF1 arrives here
         wp, gate = self._scorer_params()
         ps = self.word_scorer1.p_drop if self.training else 0.0
         assert ps == p or ps == 0 or p == 0, "scorer / layer-2 dropout rates are the same value in the reference"

@@ -102,9 +102,52 @@ DEBUG_TC_REPORT = False      # tests: record in LAST_GEMM_USED_TC whether the la
 LAST_GEMM_USED_TC = None
 
 # Weight gradients written straight into caller-owned buffers (the flat gradient bucket of get_b200.ddp): maps
-# parameter data_ptr -> fp32 view of the same shape. When a parameter is registered here the backward passes ACCUMULATE
+# parameter data_ptr -> (fp32 view of the same shape, weakref to the parameter). When a parameter is registered here the backward passes ACCUMULATE
 # into the view (the owner zeroes the bucket at the start of a step) and return no gradient for it.
 GRAD_SINK = {}
+
+
+def sink_of(param: torch.Tensor):
+    """Registered gradient sink of a parameter or None. Entries are (view, weakref to the parameter): an entry whose
+    parameter has died (its address may have been recycled) is dropped."""
+    ent = GRAD_SINK.get(param.data_ptr())
+    if ent is None:
+        return None
+    view, ref = ent
+    owner = ref()
+    if owner is None or owner.data_ptr() != param.data_ptr() or tuple(view.shape) != tuple(param.shape):
+        GRAD_SINK.pop(param.data_ptr(), None)
+        return None
+    if owner.grad is None or owner.grad.data_ptr() != view.data_ptr():
+        return None        # the caller re-pointed / dropped p.grad (e.g. zero_grad(set_to_none=True)): plain autograd flow
+    return view
+
+
+# Called with a tag from the backward pass when every gradient of a group of layers has been written (see grad_marker):
+# the data-parallel reducer starts the all-reduce of that chunk of the bucket on its communication stream.
+GRAD_READY_HOOK = None
+
+
+class _GradMarkerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, tag):
+        ctx.tag = tag
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        hook = GRAD_READY_HOOK
+        if hook is not None:
+            hook(ctx.tag)
+        return g, None
+
+
+def grad_marker(x: torch.Tensor, tag: str) -> torch.Tensor:
+    """Identity. In the backward pass, when the gradient of `x` arrives here every layer applied AFTER this point in the
+    forward pass has finished its backward: GRAD_READY_HOOK(tag) is called at that moment."""
+    if GRAD_READY_HOOK is None or not torch.is_grad_enabled() or not x.requires_grad:
+        return x
+    return _GradMarkerFn.apply(x, tag)
 
 
 def weights_updated(*_args, **_kwargs):
@@ -487,7 +530,7 @@ def _rows2d(t: torch.Tensor) -> torch.Tensor:
 def _grad_target(param: torch.Tensor, shape=None):
     """(destination tensor, accumulate?, returned gradient) for a weight / bias gradient: the registered sink view
     (accumulated in place, nothing returned to autograd) or a fresh tensor."""
-    sink = GRAD_SINK.get(param.data_ptr())
+    sink = sink_of(param)
     if sink is not None:
         return sink, True, None
     t = torch.empty(tuple(param.shape) if shape is None else shape, dtype=torch.float32, device=param.device)
@@ -495,14 +538,15 @@ def _grad_target(param: torch.Tensor, shape=None):
 
 
 def _ggnn_packs(H, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, gs):
-    """Packed B operands of one GGNN layer. Activation buffers keep [x | a | r*x] side by side (column blocks of Hp =
-    round_up(H, 8)), the gate-gradient buffer [dz' | dr' | dh'], so every contraction is ONE segment:
-      zr : rows [z: 0..H) [r: gs..gs+H), cols [x: Wz1|Wr1][a: Wz0|Wr0]        A = [x | a]          (K = 2 Hp)
-      h  : rows 0..H, cols [a: Wh0][r*x: Wh1]                                  A = [a | r*x]        (K = 2 Hp)
-      da : rows 0..H, cols [dz': Wz0^T][dr': Wr0^T][dh': Wh0^T]                A = [dz'|dr'|dh']    (K = 3 Hp)
-      dx : rows 0..H, cols [dz': Wz1^T][dr': Wr1^T]                            A = [dz'|dr']        (K = 2 Hp)
+    """Packed B operands of one GGNN layer. Activation buffers keep [x | a | r*x] side by side (column blocks of pitch Hp =
+    round_up(H + 1, 8): room for the ones column of the `a` block), the gate-gradient buffer [dz' | dr' | dh']; the packs
+    use the same column blocks, and every contraction runs over exact-width (K = H) segments of them:
+      zr : rows [z: 0..H) [r: gs..gs+H), col blocks [x: Wz1|Wr1][a: Wz0|Wr0]        A segments x, a
+      h  : rows 0..H, col blocks [a: Wh0][r*x: Wh1]                                  A segments a, r*x
+      da : rows 0..H, col blocks [dz': Wz0^T][dr': Wr0^T][dh': Wh0^T]                A segments dz', dr', dh'
+      dx : rows 0..H, col blocks [dz': Wz1^T][dr': Wr1^T]                            A segments dz', dr'
       drx: Wh1^T; p: Wp; pT: Wp^T."""
-    Hp = round_up(H, 8)
+    Hp = round_up(H + 1, 8)
     key = ("ggnn", gs) + tuple(planes._view_key(w) for w in (Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1))
 
     def b_zr():
@@ -533,7 +577,7 @@ class GGNNLayerFn(torch.autograd.Function):
         G, N = adj.shape[0], adj.shape[1]
         M = G * N
         H, Din = Wp.shape
-        Hp = round_up(H, 8)
+        Hp = round_up(H + 1, 8)
         dev = adj.device
         adj = adj.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
@@ -561,12 +605,12 @@ class GGNNLayerFn(torch.autograd.Function):
         h = torch.empty((M, H), **f32)
         out = torch.empty((M, H), **f32)
         pzr = pk["zr"]()
-        gemm_bp([(xar.view_cols(0, 2 * Hp), pzr.planes, 2 * Hp)], M, 2 * gs, mode=mode, epilogue=BPE_ZR, C=z, out1=r,
-                bias=pzr.bias, aux0=x, planes_out=rxP, zr=(gs, H), tn=bn)
+        gemm_bp([(xP, pzr.planes.view_cols(0, H), H), (aP, pzr.planes.view_cols(Hp, H), H)], M, 2 * gs, mode=mode,
+                epilogue=BPE_ZR, C=z, out1=r, bias=pzr.bias, aux0=x, planes_out=rxP, zr=(gs, H), tn=bn)
         ph = pk["h"]()
         op = alloc_planes(out_planes, M, H, dev) if out_planes else None
-        gemm_bp([(xar.view_cols(Hp, 2 * Hp), ph.planes, 2 * Hp)], M, H, mode=mode, epilogue=BPE_TANH_BLEND, C=out, out1=h,
-                bias=ph.bias, aux0=z, aux1=x, planes_out=op)
+        gemm_bp([(aP, ph.planes.view_cols(0, H), H), (rxP, ph.planes.view_cols(Hp, H), H)], M, H, mode=mode,
+                epilogue=BPE_TANH_BLEND, C=out, out1=h, bias=ph.bias, aux0=z, aux1=x, planes_out=op)
         ctx.save_for_backward(adj, keep, xd.t, xar.t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1)
         ctx.p_drop, ctx.seed, ctx.dims, ctx.has_feat, ctx.gs = p_drop, seed, (G, N, H, Din), feat is not None, gs
         op_t = op.t if op is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)
@@ -578,7 +622,7 @@ class GGNNLayerFn(torch.autograd.Function):
         (adj, keep, xd_t, xar_t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1) = ctx.saved_tensors
         G, N, H, Din = ctx.dims
         M = G * N
-        Hp = round_up(H, 8)
+        Hp = round_up(H + 1, 8)
         dev = dout.device
         lib = _lib.load()
         mode = gemm_mode(False)
@@ -596,9 +640,12 @@ class GGNNLayerFn(torch.autograd.Function):
                 out1=dx, planes_out=dg.view_cols(Hp, H))
         # da = dz'@Wz0 + dr'@Wr0 + dh'@Wh0
         da = torch.empty((M, H), dtype=torch.float32, device=dev)
-        gemm_bp([(dg.view_cols(0, 3 * Hp), pk["da"]().planes, 3 * Hp)], M, H, mode=mode, C=da)
+        dzP, drP, dhP = dg.view_cols(0, H), dg.view_cols(Hp, H), dg.view_cols(2 * Hp, H)
+        pda, pdx = pk["da"]().planes, pk["dx"]().planes
+        gemm_bp([(dzP, pda.view_cols(0, H), H), (drP, pda.view_cols(Hp, H), H), (dhP, pda.view_cols(2 * Hp, H), H)], M, H,
+                mode=mode, C=da)
         # dx += dz'@Wz1 + dr'@Wr1 + adj'^T @ da ; the aggregation kernel also writes the planes of the final dx
-        gemm_bp([(dg.view_cols(0, 2 * Hp), pk["dx"]().planes, 2 * Hp)], M, H, mode=mode, C=dx, accumulate=True)
+        gemm_bp([(dzP, pdx.view_cols(0, H), H), (drP, pdx.view_cols(Hp, H), H)], M, H, mode=mode, C=dx, accumulate=True)
         dxP = alloc_planes(mode, M, H, dev)
         graph_aggregate(adj, da.view(G, N, H), keep, out=dx.view(G, N, H), transpose=True, accumulate=True, planes_out=dxP)
         need = ctx.needs_input_grad
@@ -611,18 +658,18 @@ class GGNNLayerFn(torch.autograd.Function):
             for i_w, i_b0, i_b1, r0, W, b0, b1 in ((9, 10, 12, 0, Wz0, bz0, bz1), (13, 14, 16, Hp, Wr0, br0, br1),
                                                    (17, 18, 20, 2 * Hp, Wh0, bh0, bh1)):
                 t, acc, g = _grad_target(W)
-                assert acc == bool(GRAD_SINK), "grad sinks must cover all GGNN parameters or none"
+                assert acc == (sink_of(Wz0) is not None), "grad sinks must cover all parameters of a GGNN layer or none"
                 dsts.append((t, r0, H, 0, H)); grads[i_w] = g
                 for i_b, bb in ((i_b0, b0), (i_b1, b1)):
                     t, _, g = _grad_target(bb)
                     dsts.append((t, r0, H, H, 1)); grads[i_b] = g
-            wgrad_bp(dg.view_cols(0, 3 * Hp).T(), aP1.T(), 3 * Hp, Hp, M, mode, dsts, accumulate=bool(GRAD_SINK))
+            wgrad_bp(dg.view_cols(0, 3 * Hp).T(), aP1.T(), 3 * Hp, Hp, M, mode, dsts, accumulate=sink_of(Wz0) is not None)
         if need[11] or need[15]:
             dsts = []
             for i_w, r0, W in ((11, 0, Wz1), (15, Hp, Wr1)):
                 t, acc, g = _grad_target(W)
                 dsts.append((t, r0, H, 0, H)); grads[i_w] = g
-            wgrad_bp(dg.view_cols(0, 2 * Hp).T(), xP.T(), 2 * Hp, H, M, mode, dsts, accumulate=bool(GRAD_SINK))
+            wgrad_bp(dg.view_cols(0, 2 * Hp).T(), xP.T(), 2 * Hp, H, M, mode, dsts, accumulate=sink_of(Wz1) is not None)
         if need[19]:
             t, acc, g = _grad_target(Wh1)
             grads[19] = g
@@ -841,7 +888,7 @@ class ConcatAttFn(torch.autograd.Function):
             dW2 = torch.empty((Cn, H), **f32)
             gemm([(de.t(), t.t())], dW2)
         if need[3]:
-            sink = GRAD_SINK.get(W1.data_ptr())
+            sink = sink_of(W1)
             dW1 = sink if sink is not None else torch.empty((H, X + Dr), **f32)
             if sink is None and left is None:
                 pass
@@ -890,8 +937,8 @@ class LinearFn(torch.autograd.Function):
             gemm([(dy2, W.t())], dx)
             dx = dx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            dW = torch.empty_like(W)
-            gemm([(dy2.t(), x2.t())], dW)
+            dst, acc, dW = _grad_target(W)
+            gemm([(dy2.t(), x2.t())], dst, accumulate=acc)
         if ctx.needs_input_grad[2]:
             db = colsum(dy2)
         return dx, dW, db

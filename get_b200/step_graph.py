@@ -77,6 +77,24 @@ def pad_batch(batch: Dict, multiple: int) -> Dict:
     return out
 
 
+def slice_batch(batch: Dict, lo: int, hi: int) -> Dict:
+    """Claims [lo, hi) of a numpy mini-batch in the fitter's flattened layout (this rank's shard of a global batch): per-claim
+    arrays are sliced by claim, the flattened evidence arrays by the prefix sums of the evidence counts."""
+    cnt = np.asarray(batch[K.EvidenceCountPerQuery]).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(cnt)])
+    r0, r1 = int(off[lo]), int(off[hi])
+    out = dict(batch)
+    for k in ("query", "document", "labels", K.Query_lens, K.Query_Adj, K.QuerySources, K.DocSources, K.Doc_lens,
+              K.EvidenceCountPerQuery, "raw_query_tokens", "raw_query_lens"):
+        if k in batch:
+            out[k] = batch[k][lo:hi]
+    for k in (K.DocContentNoPaddingEvidence, K.Evd_Docs_Adj, "e_lens", "raw_doc_tokens", "raw_doc_lens"):
+        if k in batch:
+            out[k] = batch[k][r0:r1]
+    out["pairs"] = r1 - r0
+    return out
+
+
 def token_batch_to_host(batch: Dict, pin: bool = True):
     """The compact host-side form of a mini-batch: raw token ids + counts + sources + labels, a few
     hundred kB instead of the 18.8 MB of dense float64 adjacencies. Returns a dict of (pinned) CPU tensors."""
@@ -112,7 +130,7 @@ def device_batch_from_tokens(tb: Dict, device):
 
 
 class _Slot(object):
-    __slots__ = ("graph", "query", "document", "labels", "kw", "loss", "logits", "n_real", "launches")
+    __slots__ = ("graph", "query", "document", "labels", "kw", "loss", "logits", "n_real", "launches", "global_claims")
 
 
 class CapturedTrainStep(object):
@@ -133,19 +151,28 @@ class CapturedTrainStep(object):
         self.device = next(model.parameters()).device
         if reducer is not None:
             reducer.init_collective()    # communicator created here, never inside a capture
+            if not reducer.attached:
+                reducer.attach()         # the flat bucket becomes the gradient storage (weight-gradient kernels write into it)
         self.replayed_launches = 0       # kernels of libget_b200.so launched through graph replays so far
 
     # ---------------------------------------------------------------------------------------------------------
-    def _key(self, query, document, kw, n_real):
+    def _key(self, query, document, kw, n_real, global_claims=0):
         return (tuple(query.shape), tuple(document.shape), tuple(kw[K.DocContentNoPaddingEvidence].shape),
-                tuple(kw[K.Evd_Docs_Adj].shape), str(kw[K.Evd_Docs_Adj].dtype), int(n_real), bool(self.model.training))
+                tuple(kw[K.Evd_Docs_Adj].shape), str(kw[K.Evd_Docs_Adj].dtype), int(n_real), bool(self.model.training),
+                int(global_claims))
 
     def _eager(self, s: _Slot, collective: bool = True):
+        red = self.reducer
+        in_step = collective and not self.split_tail
+        if red is not None:
+            red.overlap = in_step              # chunk all-reduces are issued from the backward pass
+            # the local loss is a mean over the LOCAL claims: re-weight unequal shards
+            red.set_weight(s.n_real * red.world / s.global_claims if (s.global_claims and red.world > 1) else 1.0)
         logits = self.model(s.query, s.document, **s.kw)
         loss = self.loss_fn(logits[:s.n_real], s.labels[:s.n_real])
         loss.backward()
-        if self.reducer is not None:
-            self.reducer.reduce(collective=collective and not self.split_tail)
+        if red is not None:
+            red.reduce(collective=in_step)
         if self.optimizer is not None and not self.split_tail:
             self.optimizer.step()
         return logits, loss
@@ -156,10 +183,11 @@ class CapturedTrainStep(object):
         if self.optimizer is not None:
             self.optimizer.step()
 
-    def _build(self, query, document, labels, kw, n_real) -> _Slot:
+    def _build(self, query, document, labels, kw, n_real, global_claims=0) -> _Slot:
         dev = self.device
         s = _Slot()
         s.n_real = int(n_real)
+        s.global_claims = int(global_claims)
         new = lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev)
         s.query, s.document, s.labels = new(query), new(document), new(labels)
         s.kw = dict(kw)
@@ -176,10 +204,12 @@ class CapturedTrainStep(object):
         params = [p for p in self.model.parameters()]
         backup = [p.detach().clone() for p in params]
         # optimizer state is restored IN PLACE: graphs captured earlier hold the addresses of these tensors
-        opt_backup = None
+        opt_backup = flat_backup = None
         if self.optimizer is not None:
             opt_backup = {p: {k: (v.detach().clone() if torch.is_tensor(v) else copy.deepcopy(v)) for k, v in st.items()}
                           for p, st in self.optimizer.state.items()}
+            if hasattr(self.optimizer, "state_tensors"):        # get_b200.ddp.FlatAdam: flat moment buffers + device step
+                flat_backup = [t.detach().clone() for t in self.optimizer.state_tensors()]
         salt = ops.dropout_salt_get()
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -204,6 +234,11 @@ class CapturedTrainStep(object):
                                 v.zero_()          # state created by the warm-up step: back to its initial value
                         elif old is not None and k in old:
                             st[k] = old[k]
+            if flat_backup is not None:
+                with torch.no_grad():
+                    for t, b in zip(self.optimizer.state_tensors(), flat_backup):
+                        t.copy_(b)
+                ops.weights_updated()
         ops.dropout_salt_set(salt)
         # ---- capture
         ops.prepare_split_table()      # host -> device copy of the weight-split job table: not allowed inside the capture
@@ -214,6 +249,8 @@ class CapturedTrainStep(object):
         with torch.cuda.graph(g):
             ops.begin_step_capture()
             ops.dropout_salt_advance()
+            if self.reducer is not None and self.reducer.attached:
+                self.reducer.zero()        # part of the replayed step: gradients accumulate into the bucket
             s.logits, s.loss = self._eager(s)
         s.launches = _lib.launch_count() - n0      # kernels of libget_b200.so recorded in this graph
         ops.PROFILE_GSL_EVENTS = prof
@@ -221,7 +258,9 @@ class CapturedTrainStep(object):
         return s
 
     def _zero_grad(self):
-        if self.optimizer is not None:
+        if self.reducer is not None and self.reducer.attached:
+            self.reducer.zero()            # p.grad are views of the flat bucket: one memset, the views stay in place
+        elif self.optimizer is not None:
             self.optimizer.zero_grad(set_to_none=True)
         else:
             self.model.zero_grad(set_to_none=True)
@@ -237,12 +276,14 @@ class CapturedTrainStep(object):
         s.kw[K.DocLensIndices][2].copy_(kw[K.DocLensIndices][2], non_blocking=True)
 
     # ---------------------------------------------------------------------------------------------------------
-    def step(self, query, document, labels, kw, n_real_claims: Optional[int] = None) -> torch.Tensor:
+    def step(self, query, document, labels, kw, n_real_claims: Optional[int] = None, global_claims: int = 0) -> torch.Tensor:
+        """global_claims (multi-GPU, unequal shards): real claims of the GLOBAL batch; the local gradients are re-weighted by
+        n_real * world / global_claims so that the all-reduced average is the gradient of the global-batch mean loss."""
         n_real = int(n_real_claims if n_real_claims is not None else query.shape[0])
-        key = self._key(query, document, kw, n_real)
+        key = self._key(query, document, kw, n_real, global_claims)
         s = self.slots.get(key)
         if s is None:
-            s = self._build(query, document, labels, kw, n_real)
+            s = self._build(query, document, labels, kw, n_real, global_claims)
             self.slots[key] = s
             # the capture itself executes nothing: fall through and replay once so that this call IS a step
         else:
@@ -251,6 +292,10 @@ class CapturedTrainStep(object):
         self.replayed_launches += s.launches
         if self.split_tail:
             self._tail()
+        elif self.optimizer is not None:
+            # the replay changed the weights on the device without any host-side trace (no version counter, no optimizer
+            # hook): mark every packed weight stale so that an EAGER forward issued next (evaluation) re-packs them
+            ops.weights_updated()
         return s.loss
 
     # ---------------------------------------------------------------------------------------------------------
@@ -294,11 +339,11 @@ class CapturedTrainStep(object):
         kw_dev[K.DocLensIndices] = (None, None, st["e_lens"])
         return (st, kw_dev)
 
-    def step_prefetched(self, handle, n_real_claims: Optional[int] = None) -> torch.Tensor:
+    def step_prefetched(self, handle, n_real_claims: Optional[int] = None, global_claims: int = 0) -> torch.Tensor:
         """Call order for full overlap: loss = step_prefetched(h_i); h_next = prefetch(batch_{i+1}); read loss."""
         st, kw_dev = handle
         torch.cuda.current_stream().wait_event(st["event"])
-        loss = self.step(st["query"], st["document"], st["labels"], kw_dev, n_real_claims)
+        loss = self.step(st["query"], st["document"], st["labels"], kw_dev, n_real_claims, global_claims)
         if st.get("consumed") is None:
             st["consumed"] = torch.cuda.Event()
         st["consumed"].record()       # (recorded after the replay: a little late, but it never delays the next-but-one copy)

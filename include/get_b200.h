@@ -104,8 +104,10 @@ int get_gemm_f32_launches(const get_gemm_desc* desc);
  * `Linear` of GGNN / attention and of their backward passes (same reference call sites as get_gemm_f32).
  *
  * A fp32 value v is carried as up to three bf16 planes p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1).
- * A plane tensor is bf16 [planes][rows][ld] (ld % 8 == 0, plane_stride % 8 == 0, 16-byte aligned); columns between
- * the logical width and ld are padding the PRODUCER writes (zeros, or 1.0 in the first pad column when `pad_one`).
+ * A plane tensor is bf16 [planes][rows][ld] (ld % 8 == 0, plane_stride % 8 == 0, 16-byte aligned). Contractions never
+ * read beyond the logical width of an operand (the TMA boxes are clipped there), so padding columns carry no contract
+ * except one: a producer asked for `pad_one` writes 1.0 in column `width` (and zeros up to the next multiple of 8) -- the
+ * "ones column" through which a weight-gradient contraction also yields the bias gradient.
  * Planes are produced by the kernels that produce the activation (GEMM epilogues, graph kernels, element-wise
  * kernels) or by get_to_planes_bf16; weights are packed once per optimizer step by get_pack_planes_multi.
  *
@@ -363,6 +365,13 @@ int get_dropout_mask_f32(float* out, int64_t numel, float p, uint32_t seed, void
  * loss (1,), dlogits (B,C) = (softmax - onehot)/B. */
 int get_cross_entropy_f32(const float* logits, const int64_t* labels, int B, int C,
                           float* loss, float* dlogits, void* stream);
+
+/* Optimizer step of the reference fitter, torch.optim.Adam(lr, weight_decay) (declare_fitter.py:57-61), over FLAT
+ * fp32 buffers of n elements (parameters, gradients, first / second moments): g' = g + wd*p; m = b1 m + (1-b1) g';
+ * v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). `step` is a device counter (float),
+ * advanced by one before use, so a captured CUDA graph replays a correct bias correction. */
+int get_adam_flat_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float* step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Word-graph construction on the device (the host code interactions.py:334-351 `convert_text` + :11-18

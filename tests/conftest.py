@@ -22,3 +22,6 @@ def _reset_dropout_salt(request):
         if torch.cuda.is_available():
             from get_b200 import ops
             ops.dropout_salt_set(0)
+            ops.GRAD_SINK.clear()
+            ops.GRAD_READY_HOOK = None
+            ops.set_precision("fp32")

@@ -132,3 +132,87 @@ def test_reduce_without_collective_only_gathers_world2_gloo():
         assert local == [float(rank + 1)] * 11
         assert reduced == [1.5] * 11
         assert aliased
+
+
+def _worker_attached(rank, world, port, q):
+    """Attached bucket (gradient storage) + unequal shards: the weighted average must equal the global-batch gradient."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from get_b200 import ops
+    from get_b200.ddp import FlatGradAllReduce
+    names = ["out.0.weight", "ggnn_with_gsl.feat_prop1.proj.linear.weight", "ggnn_with_gsl.feat_prop2.proj.linear.weight",
+             "self_att_word.linear1.weight"]
+    params = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3, 2)),
+              torch.nn.Parameter(torch.zeros(5))]
+    red = FlatGradAllReduce(params, names=names).attach()
+    # bucket order = backward completion order: head chunk, feat_prop2, feat_prop1
+    assert red.names == ["out.0.weight", "self_att_word.linear1.weight", "ggnn_with_gsl.feat_prop2.proj.linear.weight",
+                         "ggnn_with_gsl.feat_prop1.proj.linear.weight"]
+    assert red.chunks == [(0, 11), (11, 17), (17, 21)]
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
+    assert all(ops.sink_of(p) is not None for p in red.params)
+    n_local, n_global = (3, 8) if rank == 0 else (5, 8)          # claims on this rank / in the global batch
+    red.zero()
+    for i, p in enumerate(red.params):                           # "local mean" gradients: value = rank + 1 everywhere
+        p.grad.add_(float(rank + 1))
+    red.set_weight(n_local * world / n_global)
+    red.reduce()
+    want = (3 * 1.0 + 5 * 2.0) / 8                               # gradient of the global-batch mean
+    ok = all(torch.allclose(p.grad, torch.full_like(p.grad, want)) for p in red.params)
+    # dropping p.grad (zero_grad(set_to_none=True)) disables the sink for that parameter: plain autograd flow
+    red.params[0].grad = None
+    ok = ok and ops.sink_of(red.params[0]) is None and ops.sink_of(red.params[1]) is not None
+    red.detach()
+    ok = ok and ops.sink_of(red.params[1]) is None
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_attached_bucket_chunks_and_shard_weights_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_attached, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+def test_slice_batch_partitions_a_global_batch():
+    from get_b200 import synthetic
+    from get_b200.ddp import shard_claims
+    from get_b200.keywords import KeyWordSettings as K
+    from get_b200.step_graph import pad_batch, slice_batch
+    w = synthetic.get_workload("tiny", batch_claims=9)
+    b = synthetic.make_batch(w, seed=5)
+    for world in (2, 4):
+        parts = [slice_batch(b, lo, hi) for lo, hi in shard_claims(b[K.EvidenceCountPerQuery], world)]
+        assert sum(p["pairs"] for p in parts) == b["pairs"]
+        for key in (K.Evd_Docs_Adj, K.DocContentNoPaddingEvidence, "e_lens"):
+            assert np.array_equal(np.concatenate([p[key] for p in parts]), b[key])
+        for key in ("query", "labels", K.Query_Adj, K.DocSources):
+            assert np.array_equal(np.concatenate([p[key] for p in parts]), b[key])
+        for p in parts:
+            pp = pad_batch(p, 8)
+            assert pp["pairs"] % 8 == 0 and pp["n_real_claims"] == p["query"].shape[0]
+
+
+def test_classification_metrics_match_sklearn():
+    from get_b200.trainer import classification_metrics
+    sk = pytest.importorskip("sklearn.metrics")
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, 2, size=200)
+    s = rng.normal(size=200) + y
+    p = (s > 0.4).astype(int)
+    m = classification_metrics(y, p, s)
+    fpr, tpr, _ = sk.roc_curve(y, s, pos_label=1)
+    assert abs(m["auc"] - sk.auc(fpr, tpr)) < 1e-12
+    assert abs(m["f1_macro"] - sk.f1_score(y, p, average="macro")) < 1e-12
+    assert abs(m["f1_micro"] - sk.f1_score(y, p, average="micro")) < 1e-12
+    assert abs(m["precision_true_cls"] - sk.precision_score(y, p, labels=[1], average=None)[0]) < 1e-12
+    assert abs(m["recall_false_cls"] - sk.recall_score(y, p, labels=[0], average=None)[0]) < 1e-12

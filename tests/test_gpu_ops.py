@@ -298,7 +298,7 @@ def test_segment_ops_masked_mean_cross_entropy_linear():
     cnt = torch.tensor([3, 1, 5, 2])
     B, n, W = 4, 6, 20
     b1 = int(cnt.sum())
-    seg, slot, off = M._segments(cnt.to(DEV), b1, n)
+    seg, slot, off = ops.segments(cnt.to(DEV), b1, n)
     assert seg.cpu().tolist() == [0, 0, 0, 1, 2, 2, 2, 2, 2, 3, 3]
     assert slot.cpu().tolist() == [0, 1, 2, 6, 12, 13, 14, 15, 16, 18, 19]
     assert off.cpu().tolist() == [0, 3, 4, 9, 11]
