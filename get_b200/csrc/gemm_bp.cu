@@ -800,6 +800,9 @@ static int bp_plan(const get_gemm_bp_desc* d, BpCfg& cfg, BpParams& p) {
                    (p.bias == nullptr || aligned16(p.bias)),
                "get_gemm_bp: fp32 epilogue tensors must be 16-byte aligned with ld %% 4 == 0");
   if (d->planes_out) {
+    GETB_REQUIRE(d->epilogue == GET_BPE_ZR || d->ld_planes_out >= p.Npad,
+                 "get_gemm_bp: planes_out row pitch %lld is smaller than the written width %d (logical width + ones column, padded to 8)",
+                 (long long)d->ld_planes_out, p.Npad);
     GETB_REQUIRE(aligned16(d->planes_out) && (d->ld_planes_out % 8) == 0 && (p.nplanes == 1 || (d->planes_out_stride % 8) == 0) &&
                      p.nplanes >= 1 && p.nplanes <= 3,
                  "get_gemm_bp: planes_out must be 16-byte aligned with ld %% 8 == 0, plane stride %% 8 == 0, 1..3 planes");
@@ -1012,7 +1015,7 @@ extern "C" int get_to_planes_bf16(const float* src, int64_t ld_src, int rows, in
   GETB_REQUIRE((((uintptr_t)planes) & 7u) == 0 && (plane_stride % 4) == 0, "get_to_planes_bf16: planes must be 8-byte aligned");
   if (rows == 0) return 0;
   const int vec = aligned16(src) && (ld_src % 4) == 0;
-  int width = bp_round_up(cols, 8);          // written columns: the logical ones plus padding up to a multiple of 8
+  int width = bp_round_up(cols + (pad_one ? 1 : 0), 8);   // written columns: logical ones (+ ones column) padded to a multiple of 8
   if (width > ld_out) width = (int)ld_out;
   const int64_t nq = (int64_t)rows * (width / 4);
   to_planes_kernel<<<ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows, cols, reinterpret_cast<__nv_bfloat16*>(planes),

@@ -890,13 +890,10 @@ class ConcatAttFn(torch.autograd.Function):
         if need[3]:
             sink = sink_of(W1)
             dW1 = sink if sink is not None else torch.empty((H, X + Dr), **f32)
-            if sink is None and left is None:
-                pass
             if use_tc:
                 gemm([(duP, Planes(rP_t, Dr))], dW1[:, X:], tc=True, presplit=False, accumulate=sink is not None)
             else:
-                assert sink is None
-                gemm([(du.t(), right2d.t())], dW1[:, X:])
+                gemm([(du.t(), right2d.t())], dW1[:, X:], accumulate=sink is not None)
             if left is not None:
                 gemm([(du_sum.t(), left.contiguous().t())], dW1[:, :X], accumulate=sink is not None)
             if sink is not None:

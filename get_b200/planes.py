@@ -80,7 +80,7 @@ def to_planes(x: torch.Tensor, nplanes: int, pad_one: bool = False, out: Optiona
     assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and (x.stride(1) == 1 or x.shape[1] == 1)
     rows, cols = x.shape
     if out is None:
-        out = alloc_planes(nplanes, rows, cols, x.device)
+        out = alloc_planes(nplanes, rows, cols, x.device, ld=round_up(cols + (1 if pad_one else 0), 8))
     assert out.rows == rows and out.cols == cols and out.nplanes >= nplanes
     _lib.check(_lib.load().get_to_planes_bf16(x.data_ptr(), x.stride(0) if rows > 1 else max(x.stride(0), cols), rows, cols,
                                               out.ptr, out.ld, out.plane_stride, nplanes, int(pad_one), _stream()),

@@ -187,7 +187,8 @@ int get_bp_splitk_reduce(const float* workspace, int splits, int M, int64_t ws_l
                          int accumulate, void* stream);
 
 /* fp32 (rows, cols) matrix with row stride ld_src -> bf16 planes [nplanes][rows][ld_out]; the pad columns from `cols`
- * up to the next multiple of 8 (at most ld_out) are written too (zeros; 1.0 at column `cols` when pad_one). */
+ * up to the next multiple of 8 of cols (+1 with pad_one), at most ld_out, are written too (zeros; 1.0 at column `cols`
+ * when pad_one). */
 int get_to_planes_bf16(const float* src, int64_t ld_src, int rows, int cols, void* planes, int64_t ld_out,
                        int64_t plane_stride, int nplanes, int pad_one, void* stream);
 

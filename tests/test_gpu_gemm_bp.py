@@ -46,14 +46,13 @@ def test_bp_gemm_kmajor_plain(M, N, K, mode):
     wd, bd = w.to(DEV), bias.to(DEV)
     pk = P.pack_of(wd, bd)
     out = torch.empty(M, N, device=DEV)
-    po = P.alloc_planes(3, M, N, DEV)
+    po = P.alloc_planes(3, M, N, DEV, ld=P.round_up(N + 1, 8))          # room for the ones column
     P.gemm_bp([(ap, pk.planes, K)], M, N, mode=mode, C=out, bias=pk.bias, planes_out=po, planes_out_n=3, pad_one=True)
     assert _err(out, ref) <= BOUND[mode] * mag * max(1.0, K / 512.0), (mode, _err(out, ref), mag)
     # the planes written by the epilogue carry the same values (3 planes = fp32) and the padding contract
     assert float((po.to_float() - out).abs().max()) <= 2.0 ** -22 * float(out.abs().max())
-    if N % 8:
-        assert torch.equal(po.t[0, :, N].float(), torch.ones(M, device=DEV))
-        assert float(po.t[1:, :, N:].float().abs().max()) == 0.0
+    assert torch.equal(po.t[0, :, N].float(), torch.ones(M, device=DEV))          # the ones column
+    assert float(po.t[1:, :, N:].float().abs().max()) == 0.0 and float(po.t[0, :, N + 1:].float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("kblock", [32, 64])
