@@ -156,54 +156,110 @@ def emit(line: dict):
     sys.stdout.flush()
 
 
-def make_batches(w, n, base_seed):
+def make_batches(w, n, base_seed, n_claims=None):
     from get_b200 import synthetic
-    return [synthetic.make_batch(w, seed=base_seed + 1000 * i) for i in range(n)]
+    return [synthetic.make_batch(w, seed=base_seed + 1000 * i, n_claims=n_claims) for i in range(n)]
 
 
 def graph_kernel_bytes(w, pairs):
-    """ALGORITHMIC bytes of the fused GSL kernel per launch: read F1 + adjacency, write the
-    refined aggregation: 4*R*(2H+R) per pair."""
+    """ALGORITHMIC bytes of the fused GSL kernel per launch: read F1 + adjacency, write the refined
+    aggregation (two bf16 planes = 4 bytes per element, like the fp32 the formula was written for): 4*R*(2H+R) per pair."""
     return pairs * 4 * w.len_right * (2 * w.hidden + w.len_right)
 
 
+def config_dict(w):
+    """Workload description shared VERBATIM by both arms (the driver compares it)."""
+    return {"workload": "%s B=%d L=%d R=%d D=%d H=%d heads=%d/%d window=%d gsl_rate=%.1f" % (
+        w.name, w.batch_claims, w.len_left, w.len_right, w.emb_dim, w.hidden, w.heads_words, w.heads_evds, w.window,
+        w.gsl_rate),
+        "step": "forward + cross-entropy + backward + grad all-reduce (N>1) + Adam(lr=1e-4, wd=1e-3), train-mode dropout",
+        "claims_per_gpu_per_step": w.batch_claims,
+        "l2": "inputs rotate over %d distinct batches; every step also writes ~0.8 GB of activations (> 126 MB L2)" % NBATCH}
+
+
 # =================================================================================================
-def run_reference(args):
-    """The reference algorithm on the host cores (oracle port; PyTorch CPU ops, all threads)."""
+# the reference: its own unmodified modules (oracle/_ref, a verbatim copy made by oracle/make_ref.py) when available,
+# else the oracle port
+# =================================================================================================
+class _cpu_shim(object):
+    """Models/BiDAF/wrapper.py:221 hard-codes `.cuda()`: while the reference runs on the host cores `Tensor.cuda` is the
+    identity (restored afterwards, so the same process can also run the reference on the GPU)."""
+
+    def __enter__(self):
+        import torch
+        self.t, self.orig = torch, torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self_, *a, **k: self_
+
+    def __exit__(self, *exc):
+        self.t.Tensor.cuda = self.orig
+
+
+def reference_modules():
+    from oracle import ref_import        # bench.py's reference / baseline legs may execute oracle/
+    if not ref_import.available():
+        return None
+    return ref_import.import_reference()[0]
+
+
+def reference_step_fn(w, device, train=True):
+    """(step(i) -> None, forward(i) -> None, pairs per batch list): the reference's own training step -- zero_grad, forward,
+    losses.cross_entroy, backward, Adam(lr, weight_decay=1e-3) step (declare_fitter.py:57-61, char_man_fitter...:92-128)."""
     import torch
     from get_b200 import synthetic
-    from oracle import get_oracle as O       # bench.py's reference / cpu_baseline legs may execute the oracle
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    w = synthetic.get_workload(WORKLOAD)
-    res = cpu_baseline(w, steps=args.steps, warmup=args.warmup, cores=cores)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(w, extra={"device": "cpu"}),
-        "cpu_baseline": {"value": res["value"], "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": res["sample"]},
-        "e2e": {"value": res["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+    gbss = reference_modules()
+    torch.manual_seed(123756)
+    model = gbss.Graph_basedSemantiStructure(synthetic.match_params(w, cuda=(device != "cpu")))
+    model = model.to(device)
+    model.train(train)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3)
+    batches = make_batches(w, 4, 123756)
+    tens = [synthetic.batch_to_torch(b, device=device) for b in batches]
+    lossf = torch.nn.CrossEntropyLoss()           # losses.py:29-32
+
+    def step(i):
+        q, d, l, kw = tens[i % len(tens)]
+        opt.zero_grad()
+        loss = lossf(model(q, d, **kw), l.long())
+        loss.backward()
+        opt.step()
+
+    def forward(i):
+        q, d, l, kw = tens[i % len(tens)]
+        with torch.no_grad():
+            model(q, d, **kw)
+    return step, forward, [b["pairs"] for b in batches], model
 
 
 def cpu_baseline(w, steps, warmup, cores, max_seconds=40.0):
-    """Oracle (CPU restatement of the reference modules) forward + backward on the same Snopes batches."""
+    """The reference on the host cores: its own modules in train mode (kind "reference") or, when oracle/_ref is absent, the
+    oracle port (eval-mode forward + backward; kind "port")."""
     import torch
+    torch.set_num_threads(cores)
+    if reference_modules() is not None:
+        with _cpu_shim():
+            step, _, pairs_list, _ = reference_step_fn(w, "cpu", train=True)
+            pairs, t_total, done = 0, 0.0, 0
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                step(i)
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    t_total += dt
+                    pairs += pairs_list[i % len(pairs_list)]
+                    done += 1
+                    if t_total > max_seconds:
+                        break
+        return {"value": pairs / t_total, "ms_per_step": 1e3 * t_total / done, "kind": "reference",
+                "sample": "%d training steps (fwd + CE + bwd + Adam, train-mode dropout) of the UNMODIFIED reference modules on "
+                          "%s batches (B=%d), %.1f s of CPU work" % (done, w.name, w.batch_claims, t_total)}
     from get_b200 import synthetic
     from get_b200.model import Graph_basedSemantiStructure
     from oracle import get_oracle as O
-    torch.set_num_threads(cores)
     torch.manual_seed(123756)
     model = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=False))   # parameter container only (CPU)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     cfg = dict(gsl_rate=w.gsl_rate, use_claim_source=w.use_claim_source, use_article_source=w.use_article_source)
-    batches = make_batches(w, min(NBATCH, max(1, steps)), 123756)
+    batches = make_batches(w, min(4, max(1, steps)), 123756)
     tens = [synthetic.batch_to_torch(b) for b in batches]
     pairs, t_total, done = 0, 0.0, 0
     for i in range(warmup + steps):
@@ -217,60 +273,205 @@ def cpu_baseline(w, steps, warmup, cores, max_seconds=40.0):
             done += 1
             if t_total > max_seconds:
                 break
-    return {"value": pairs / t_total, "ms_per_step": 1e3 * t_total / done,
-            "sample": "%d fwd+bwd steps of the same %s batches (B=%d, eval-mode dropout), %.1f s of CPU work"
+    return {"value": pairs / t_total, "ms_per_step": 1e3 * t_total / done, "kind": "port",
+            "sample": "%d fwd+bwd steps of the oracle port on %s batches (B=%d, eval-mode dropout), %.1f s of CPU work"
                       % (done, w.name, w.batch_claims, t_total)}
 
 
-def config_dict(w, extra=None):
-    cfg = {"workload": "%s B=%d L=%d R=%d D=%d H=%d heads=%d/%d window=%d gsl_rate=%.1f" % (
-        w.name, w.batch_claims, w.len_left, w.len_right, w.emb_dim, w.hidden, w.heads_words, w.heads_evds, w.window,
-        w.gsl_rate),
-        "step": "forward + cross-entropy + backward + grad all-reduce (N>1) + Adam(lr=1e-4, wd=1e-3)",
-        "claims_per_gpu_per_step": w.batch_claims,
-        "l2": "inputs rotate over %d distinct batches; every step also writes ~0.8 GB of activations (> 126 MB L2)" % NBATCH}
-    if extra:
-        cfg.update(extra)
-    return cfg
-
-
-def stream_roofline(w, dev, graphs=7680, iters=10):
-    """The same fused kernel at streaming size (BASELINE.json configs[4]: thousands of claim-evidence graphs resident,
-    Snopes dims): at B=32 the launch is two partial waves of CTAs, SURVEY.md 8(d) asks for the roofline at B1 >= 1e4-ish
-    sizes as well. Inputs (2 x 1.2 GB sets, alternated) exceed L2; eval- and train-mode (dropout) launches."""
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, all threads."""
     import torch
-    from get_b200 import ops
-    N, H = w.len_right, w.hidden
-    rng = np.random.default_rng(7)
     from get_b200 import synthetic
-    base = []
-    for g in range(48):
-        pool = rng.integers(2, w.vocab, size=min(w.evd_pool, w.vocab - 2))
-        toks = pool[rng.integers(0, pool.shape[0], size=N)]
-        base.append(synthetic.word_graph(toks, N, w.window)[1].astype(np.float32))
-    adj1 = torch.from_numpy(np.stack(base)).to(dev)
-    sets = []
-    for s in range(2):
-        adj = adj1.repeat((graphs + 47) // 48, 1, 1)[:graphs].contiguous()
-        sets.append((adj, torch.randn(graphs, N, H, device=dev)))
-    wp, gate = torch.randn(H, device=dev) * 0.1, torch.randn(12, device=dev)
-    k = int(w.gsl_rate * N)
-    peak, _ = _peaks()
-    out = {"graphs": graphs, "algorithmic_bytes_per_launch": graphs * 4 * N * (2 * H + N), "peak": peak, "unit": "GB/s"}
-    for name, p in (("eval", 0.0), ("train_p0.2", 0.2)):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = synthetic.get_workload(args.workload)
+    res = cpu_baseline(w, steps=args.steps, warmup=args.warmup, cores=cores, max_seconds=240.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(w),
+        "cpu_baseline": {"value": res["value"], "unit": "pairs/s", "cores": cores, "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    emit(line)
+
+
+def torch_cuda_baseline(w, dev, model_ours, iters=10):
+    """north_star's '>= 10x the reference PyTorch-CUDA forward on 1xB200': the UNMODIFIED reference modules on the GPU
+    (torch eager, cuBLAS) next to ours, same batches. forward = eval mode, no_grad; fwd_bwd = the training step."""
+    import torch
+    from get_b200 import synthetic
+    from get_b200.evaluate import CapturedForward
+    if reference_modules() is None:
+        return {"unavailable": "oracle/_ref not present (run python oracle/make_ref.py in the build container)"}
+
+    def timed(fn, n):
         for i in range(3):
-            ops.gsl_fused(*sets[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2)
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    step, forward, pairs_list, ref_model = reference_step_fn(w, str(dev), train=True)
+    ref_fb = timed(step, iters)
+    ref_model.train(False)
+    ref_fwd = timed(forward, iters)
+    del ref_model
+    batches = make_batches(w, 4, 123756)
+    tens = [synthetic.batch_to_torch(b, device=dev) for b in batches]
+    was = model_ours.training
+    model_ours.train(False)
+    cap = CapturedForward(model_ours)
+    ours_fwd = timed(lambda i: cap.forward(tens[i % 4][0], tens[i % 4][1], tens[i % 4][3]), 4 * iters)
+    model_ours.train(was)
+    return {"reference_forward_ms": ref_fwd, "reference_fwd_bwd_adam_ms": ref_fb, "ours_forward_ms": ours_fwd,
+            "forward_speedup": ref_fwd / ours_fwd, "pairs_per_batch": float(np.mean(pairs_list)),
+            "note": "unmodified reference modules (.cuda(), torch eager) vs ours (captured forward), eval-mode forward over the "
+                    "same 4 batches; fwd_bwd = zero_grad + forward + CE + backward + Adam in train mode"}
+
+
+def stream_roofline(w, dev, graphs=7680, iters=10, sweep=False):
+    """The fused GSL kernel at streaming size (BASELINE.json configs[4]: thousands of claim-evidence graphs resident, Snopes
+    dims; SURVEY.md 8(d) asks for the roofline at B1 >= 1e4-ish sizes too). Inputs (2 sets, alternated) exceed L2.
+    sweep=True: gnn_window_size in {3,5,9} x gsl_rate in {0.3,0.6,0.9} (train-mode launches)."""
+    import torch
+    from get_b200 import ops, synthetic
+    N, H = w.len_right, w.hidden
+    peak, _ = _peaks()
+    wp, gate = torch.randn(H, device=dev) * 0.1, torch.randn(12, device=dev)
+    npl = ops.gemm_mode(False)
+
+    def adj_set(window):
+        rng = np.random.default_rng(7 + window)
+        base = []
+        for g in range(48):
+            pool = rng.integers(2, w.vocab, size=min(w.evd_pool, w.vocab - 2))
+            toks = pool[rng.integers(0, pool.shape[0], size=N)]
+            base.append(synthetic.word_graph(toks, N, window)[1].astype(np.float32))
+        a1 = torch.from_numpy(np.stack(base)).to(dev)
+        return a1.repeat((graphs + 47) // 48, 1, 1)[:graphs].contiguous(), float(np.mean([(b != 0).sum() for b in base]))
+
+    feats = [torch.randn(graphs, N, H, device=dev) for _ in range(2)]
+
+    def run(adj, k, p):
+        for i in range(3):
+            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl)
         evs = []
         for i in range(iters):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            ops.gsl_fused(*sets[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2)
+            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl)
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-        gbs = out["algorithmic_bytes_per_launch"] / ms / 1e6
-        out[name] = {"avg_launch_ms": ms, "achieved": gbs, "frac": gbs / peak}
+        return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    nbytes = graphs * 4 * N * (2 * H + N)
+    out = {"graphs": graphs, "algorithmic_bytes_per_launch": nbytes, "peak": peak, "unit": "GB/s"}
+    adj, nnz = adj_set(w.window)
+    for name, p in (("eval", 0.0), ("train_p0.2", 0.2)):
+        ms = run(adj, int(w.gsl_rate * N), p)
+        out[name] = {"avg_launch_ms": ms, "achieved": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+    if sweep:
+        rows = []
+        for window in (3, 5, 9):
+            adj, nnz = adj_set(window)
+            for rate in (0.3, 0.6, 0.9):
+                ms = run(adj, int(rate * N), 0.2)
+                rows.append({"gnn_window_size": window, "gsl_rate": rate, "nnz_per_graph": nnz, "avg_launch_ms": ms,
+                             "achieved": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak})
+        out["sweep_train"] = rows
+    return out
+
+
+def build_trainer(w, dev, precision, use_graph=True, flat_adam=True, micro=False):
+    """Model + gradient bucket (the gradient storage) + Adam + captured step for workload w."""
+    import torch
+    from get_b200 import ops, synthetic
+    from get_b200.ddp import FlatAdam, FlatGradAllReduce, trainable_named_parameters
+    from get_b200.model import Graph_basedSemantiStructure
+    from get_b200.step_graph import CapturedTrainStep
+    ops.set_precision(precision)
+    torch.manual_seed(123756)
+    model = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=True)).to(dev)
+    model.train()
+    named = trainable_named_parameters(model)
+    reducer = FlatGradAllReduce([p for _, p in named], names=[n for n, _ in named])
+    if flat_adam:
+        opt = FlatAdam(reducer, lr=1e-4, weight_decay=1e-3)
+    else:
+        opt = torch.optim.Adam([p for _, p in named], lr=1e-4, weight_decay=1e-3, fused=True, capturable=use_graph)
+    stepper = None
+    if use_graph:
+        stepper = CapturedTrainStep(model, None if micro else opt, reducer, accumulate=micro,
+                                    collective_in_graph=os.environ.get("GET_B200_GRAPH_COLLECTIVE", "1") != "0")
+    else:
+        reducer.attach()
+    return model, reducer, opt, stepper
+
+
+def extra_workload(name, dev, precision, steps, warmup):
+    """Short single-GPU measurement of another BASELINE.json config with the same step definition (extra keys of the line)."""
+    import torch
+    from get_b200 import _lib, ops, synthetic
+    from get_b200.step_graph import pad_batch
+    w = synthetic.get_workload(name)
+    micro = name == "synthetic512"
+    if micro:
+        # configs[3]: B=512 claims x 30 evidences (15 360 pairs), R=200, D=H=512, 8 word heads. One optimizer step =
+        # 16 micro-batches of 32 claims whose gradients accumulate in the bucket (the activations of all 3.07 M graph
+        # rows at once would not fit), then one Adam step. The micro-batches alternate between 2 distinct synthetic ones.
+        mb = 32
+        model, reducer, opt, stepper = build_trainer(w, dev, precision, micro=True)
+        batches = make_batches(w, 2, 777, n_claims=mb)
+        tens = [synthetic.batch_to_torch(b, device=dev, adj_dtype=torch.float32) for b in batches]
+        n_micro = w.batch_claims // mb
+        stepper.loss_scale = 1.0 / n_micro
+
+        def step(i):
+            reducer.zero()
+            for j in range(n_micro):
+                loss = stepper.step(*tens[(i + j) % 2], mb)
+            reducer.reduce()
+            opt.step()
+            return loss
+        pairs_per_step = float(np.mean([b["pairs"] for b in batches])) * n_micro
+    else:
+        model, reducer, opt, stepper = build_trainer(w, dev, precision)
+        batches = [pad_batch(b, PAD_PAIRS) for b in make_batches(w, 8, 4242)]
+        tens = [synthetic.batch_to_torch(b, device=dev) for b in batches]
+
+        def step(i):
+            b = batches[i % 8]
+            return stepper.step(*tens[i % 8], b["n_real_claims"])
+        pairs_per_step = float(np.mean([b["real_pairs"] for b in batches]))
+    for i in range(max(warmup, 8 if not micro else 1)):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"config": config_dict(w), "precision": precision, "dtype": "bf16" if precision == "bf16" else "f32", "steps": steps,
+           "ms_per_step": ms, "value": pairs_per_step / ms * 1e3, "unit": "pairs/s", "pairs_per_step": pairs_per_step,
+           "loss_finite": bool(torch.isfinite(loss).item()), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    if micro:
+        out["micro_batches"] = "%d x %d claims per optimizer step" % (w.batch_claims // 32, 32)
+    reducer.detach()
+    del model, reducer, opt, stepper, tens
+    torch.cuda.empty_cache()
     return out
 
 
@@ -279,9 +480,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from get_b200 import _lib, ops, synthetic
-    from get_b200.ddp import FlatGradAllReduce, trainable_named_parameters
+    from get_b200.ddp import shard_claims
     from get_b200.keywords import KeyWordSettings as K
-    from get_b200.model import Graph_basedSemantiStructure
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference)")
@@ -294,27 +494,25 @@ def run_ours(args):
         # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") and logs go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    w = synthetic.get_workload(WORKLOAD)
-    ops.set_precision(args.precision)
-    torch.manual_seed(123756)
-    model = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=True)).to(dev)
-    model.train()
-    named = trainable_named_parameters(model)
-    params = [p for _, p in named]
+    w = synthetic.get_workload(args.workload)
     use_graph = not args.no_graph
-    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-3, fused=True, capturable=use_graph)
-    reducer = FlatGradAllReduce(params)
+    if args.workload == "synthetic512":
+        if rank == 0:
+            res = extra_workload("synthetic512", dev, args.precision, max(1, min(args.steps, 3)), 1)
+            emit({"metric": METRIC, "value": res["value"], "unit": "pairs/s", "n_gpus": 1, "steps": res["steps"], "warmup": 1,
+                  "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                  "dtype": res["dtype"], "data": "synthetic", "config": res["config"], "detail": res})
+        return
+    model, reducer, opt, stepper = build_trainer(w, dev, args.precision, use_graph=use_graph, flat_adam=not args.torch_adam)
 
-    batches = make_batches(w, NBATCH, 123756 + 7919 * rank)
-    if use_graph:
-        # one CUDA graph per batch shape: pad the flattened pairs to a multiple of PAD_PAIRS with dummy claims that are
-        # excluded from the loss (get_b200/step_graph.py); `pairs` below keeps counting REAL pairs only
-        from get_b200.step_graph import CapturedTrainStep, pad_batch
-        padded = [pad_batch(b, PAD_PAIRS) for b in batches]
-        stepper = CapturedTrainStep(model, opt, reducer,
-                                    collective_in_graph=os.environ.get("GET_B200_GRAPH_COLLECTIVE", "1") != "0")
-    else:
-        padded = batches
+    # every rank generates the same GLOBAL batches (world x 32 claims) and takes its claim shard, balanced by evidence count
+    from get_b200.step_graph import pad_batch, slice_batch
+    glob = make_batches(w, NBATCH, 123756, n_claims=w.batch_claims * world)
+    bounds = [shard_claims(g[K.EvidenceCountPerQuery], world)[rank] for g in glob]
+    batches = [slice_batch(g, lo, hi) for g, (lo, hi) in zip(glob, bounds)]
+    gclaims = [g["query"].shape[0] if world > 1 else 0 for g in glob]
+    del glob
+    padded = [pad_batch(b, PAD_PAIRS) for b in batches] if use_graph else batches
     n_real = [b.get("n_real_claims", b["query"].shape[0]) for b in padded]
     host = [synthetic.batch_to_torch(b, device="cpu", pin=True) for b in padded]
     resident = [synthetic.batch_to_torch(b, device=dev) for b in padded]
@@ -334,17 +532,20 @@ def run_ours(args):
                     n += x.numel() * x.element_size()
         return n
 
-    def step(db, b):
+    def eager_step(db, b):
         q, d, l, kw = db
-        if use_graph:
-            return stepper.step(q, d, l, kw, n_real[b])      # copies into the graph's static buffers, one replay
-        opt.zero_grad(set_to_none=True)
+        reducer.zero()
         logits = model(q, d, **kw)
-        loss = ops.cross_entropy(logits, l)
+        loss = ops.cross_entropy(logits[:n_real[b]], l[:n_real[b]])
         loss.backward()
         reducer.reduce()
         opt.step()
         return loss
+
+    def step(db, b):
+        if use_graph:
+            return stepper.step(*db, n_real[b], global_claims=gclaims[b])      # copies into static buffers, one replay
+        return eager_step(db, b)
 
     def barrier():
         if world > 1:
@@ -390,7 +591,7 @@ def run_ours(args):
         for i in range(nsteps):
             b = (i + args.warmup) % NBATCH
             if use_graph:
-                loss = stepper.step_prefetched(nxt, n_real[b])             # device-to-device copy-in + one graph replay
+                loss = stepper.step_prefetched(nxt, n_real[b], gclaims[b])    # device-to-device copy-in + one graph replay
                 if i + 1 < nsteps:                                         # H2D of the next batch while this step runs
                     nxt = stepper.prefetch(*host[(i + 1 + args.warmup) % NBATCH])
             else:
@@ -435,7 +636,7 @@ def run_ours(args):
     # ---- timed region 3: end to end from the COMPACT host format (token ids instead of dense float64
     #      adjacencies; the word graphs are built on the device by get_build_word_graphs) -----------------------------
     e2e_tok = None
-    if use_graph:
+    if use_graph and world == 1:
         from get_b200.step_graph import device_batch_from_tokens, token_batch_to_host
         tbs = [token_batch_to_host(b) for b in padded]
         tok_bytes = [sum(v.numel() * v.element_size() for v in tb.values() if torch.is_tensor(v)) for tb in tbs]
@@ -461,18 +662,18 @@ def run_ours(args):
                    "note": "host sends raw token ids; node lists and normalised adjacencies are built on the GPU"}
 
     # ---- roofline of the fused GSL kernel: the same steps issued kernel by kernel (events cannot be read out of a graph
-    #      replay), CUDA events on the launch stream around every get_gsl_fused_f32 launch ------------------------------
-    gsl_ms, gsl_pairs, stream_roof = [], [], None
+    #      replay), CUDA events on the launch stream around every fused GSL launch --------------------------------------
+    gsl_ms, gsl_pairs, stream_roof, tcb, extra = [], [], None, None, {}
     if rank == 0:
         # (1) the same steps issued kernel by kernel, recording the arguments of every fused GSL launch
         ops.PROFILE_GSL_ARGS = []
+        reducer.overlap = False
         for i in range(min(args.steps, NBATCH)):
             b = (i + args.warmup) % NBATCH
             q, d, l, kw = resident[b]
-            opt.zero_grad(set_to_none=True)
+            reducer.zero()
             loss = ops.cross_entropy(model(q, d, **kw)[:n_real[b]], l[:n_real[b]])
             loss.backward()
-            opt.step()
         torch.cuda.synchronize()
         recs, ops.PROFILE_GSL_ARGS = ops.PROFILE_GSL_ARGS, None
         # (2) exactly those launches (same adjacency / layer-1 features / dropout seeds, ~60 MB of distinct inputs each,
@@ -481,13 +682,17 @@ def run_ours(args):
         for rep in range(3):
             e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e_a.record()
-            npairs = [ops.gsl_fused_replay(r) for r in recs]
+            ngraphs = [ops.gsl_fused_replay(r) for r in recs]
             e_b.record()
             torch.cuda.synchronize()
             if rep > 0:
                 gsl_ms.append(e_a.elapsed_time(e_b) / len(recs))
-                gsl_pairs.append(float(np.mean(npairs)))
-        stream_roof = stream_roofline(w, dev)
+                gsl_pairs.append(float(np.mean(ngraphs)))
+        real_pairs = float(np.mean([batches[(i + args.warmup) % NBATCH]["pairs"] for i in range(min(args.steps, NBATCH))]))
+        del recs
+        if world == 1 and not args.quick:
+            stream_roof = stream_roofline(w, dev, sweep=True)
+            tcb = torch_cuda_baseline(w, dev, model)
     barrier()
 
     # ---- reduce over ranks: max time, summed pairs ------------------------------------------------
@@ -497,13 +702,21 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = stats.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmin = stats.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        rank_spread = {"t_dev_max_s": float(tmax[0]), "t_dev_min_s": float(tmin[0]), "pairs_max": float(tmax[2]), "pairs_min": float(tmin[2])}
         t_dev, t_e2e = float(tmax[0]), float(tmax[1])
         pairs, pairs_e2e = float(tsum[2]), float(tsum[3])
+    else:
+        rank_spread = None
 
+    stepper_graphs = stepper.n_graphs() if use_graph else 0
     if rank == 0:
         peak, peak_src = _peaks()
         gsl_avg_ms = float(np.mean(gsl_ms)) if gsl_ms else None
-        gsl_bytes = float(np.mean([graph_kernel_bytes(w, n) for n in gsl_pairs])) if gsl_pairs else None
+        # algorithmic bytes on the REAL pairs of the batches (the launches also carry the dummy pairs that pad the batch to a
+        # multiple of 16: they are work of the launch but not of the workload)
+        gsl_bytes = float(graph_kernel_bytes(w, real_pairs)) if gsl_ms else None
         achieved = gsl_bytes / (gsl_avg_ms * 1e-3) / 1e9 if gsl_ms else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gsl_fused_traffic.json")
@@ -514,32 +727,51 @@ def run_ours(args):
         if world == 1:                 # the CPU baseline is an N=1 measurement (other ranks' host threads would disturb it)
             cores = os.cpu_count() or 1
             cpu = cpu_baseline(w, steps=5, warmup=1, cores=cores, max_seconds=25.0)
+            if not args.quick and args.workload == "snopes":
+                # the other BASELINE.json configs, same step definition, short single-GPU runs
+                reducer.detach()
+                del stepper, opt
+                torch.cuda.empty_cache()
+                for name, prec, k in (("politifact", "bf16", 20), ("politifact", "fp32", 20), ("synthetic512", "fp32", 2)):
+                    try:
+                        extra["%s_%s" % (name, prec)] = extra_workload(name, dev, prec, k, 3)
+                    except Exception as e:  # noqa: BLE001 -- an extra must never take the headline line down
+                        extra["%s_%s" % (name, prec)] = {"error": str(e).splitlines()[-1][:300]}
+                ops.set_precision(args.precision)
         line = {
             "metric": METRIC, "value": pairs / t_dev, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "tf32 (single tensor-core pass outside the top-k chain; 1e-2 parity class)",
+            "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
-            "config": config_dict(w, {"parallelism": "dp%d" % world, "precision": args.precision, "mean_pairs_per_step_per_gpu": pairs / args.steps / world,
-                                      "grad_allreduce_bytes": reducer.nbytes if world > 1 else 0,
-                                      "wall_s_timed_region": t_wall,
-                                      "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps}),
+            "config": config_dict(w),
+            "run": {"parallelism": "dp%d" % world, "precision": args.precision,
+                    "precision_note": {"fp32": "16-bit bf16-plane operands (3 tensor-core products), fp32-exact class (6 products) on the GSL top-k chain",
+                                       "fp32x": "fp32-exact class everywhere", "bf16": "plain bf16 operands, fp32-exact class on the GSL top-k chain"}[args.precision],
+                    "mean_pairs_per_step_per_gpu": pairs / args.steps / world,
+                    "grad_allreduce_bytes": reducer.nbytes if world > 1 else 0, "grad_allreduce": "3 chunks overlapped with the backward pass" if world > 1 else None,
+                    "claims_sharding": "global batch of %d claims sharded by evidence count" % (w.batch_claims * world) if world > 1 else None,
+                    "rank_spread": rank_spread, "wall_s_timed_region": t_wall, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps,
+                    "optimizer": "torch.optim.Adam(fused)" if args.torch_adam else "get_adam_flat_f32 (one kernel over the flat bucket)"},
             "clocks": clocks,
             "e2e": {"value": pairs_e2e / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "passes_ms_per_step": [1e3 * t / args.steps for t in e2e_times], "reported": "median of 3 passes of K steps"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "graph_smem_kernel<FUSED=1> (get_gsl_fused_f32), train-mode dropout, the bench batches' own launches replayed back to back",
+            "roofline": {"kernel": "fused GSL graph kernel (get_gsl_fused_bp), train-mode dropout, the bench batches' own launches replayed back to back",
                          "bound": "hbm", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "avg_launch_ms": gsl_avg_ms, "algorithmic_bytes_per_launch": gsl_bytes,
+                         "bytes_counted_on": "real pairs (%.1f per launch; launches carry %.1f incl. padding)" % (real_pairs, float(np.mean(gsl_pairs)) if gsl_pairs else 0.0),
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
             "e2e_token_inputs": e2e_tok,
             "h2d_diagnostic": h2d_diag,
             "roofline_stream": stream_roof,
-            "cuda_graphs": {"enabled": use_graph, "graphs": stepper.n_graphs() if use_graph else 0, "pad_pairs_to": PAD_PAIRS if use_graph else 0},
-            "cpu_baseline": ({"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+            "torch_cuda_baseline": tcb,
+            "extra": extra or None,
+            "cuda_graphs": {"enabled": use_graph, "graphs": stepper_graphs, "pad_pairs_to": PAD_PAIRS if use_graph else 0},
+            "cpu_baseline": ({"value": cpu["value"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": cpu["kind"],
                               "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]} if cpu is not None else None),
         }
         emit(line)
@@ -559,14 +791,20 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fast"],
-                    help="fp32 = 3xTF32 everywhere (the judged configuration); fast = single tf32 pass outside the GSL top-k chain")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["snopes", "politifact", "synthetic512", "stream"],
+                    help="BASELINE.json configs: snopes (configs[0]/[1], the headline), politifact (configs[2]), synthetic512 "
+                         "(configs[3], micro-batched), stream (configs[4] shape)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32x", "bf16", "fast"],
+                    help="fp32 = 16-bit plane operands outside the GSL top-k chain (the judged 1e-4 configuration); fp32x = "
+                         "fp32-exact class everywhere; bf16 = plain bf16 operands outside the chain (1e-2 class)")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused) instead of the in-tree flat Adam kernel")
+    ap.add_argument("--quick", action="store_true", help="skip the extras (other workloads, stream sweep, torch-CUDA baseline)")
     args = ap.parse_args()
+    if args.precision == "fast":
+        args.precision = "bf16"
     guard_stdout()
     if args.impl == "reference":
-        if args.steps > 12:
-            args.steps = 12          # bounded sample: ~1 s of CPU work per step
         run_reference(args)
     else:
         run_ours(args)

@@ -141,8 +141,15 @@ class CapturedTrainStep(object):
     Multi-GPU: every call of step() executes exactly one gradient all-reduce (inside the replayed graph), whether or not
     the shape is new on this rank, so ranks stay in lock-step as long as they call step() equally often."""
 
-    def __init__(self, model, optimizer=None, reducer=None, loss_fn=None, collective_in_graph: bool = True):
+    def __init__(self, model, optimizer=None, reducer=None, loss_fn=None, collective_in_graph: bool = True,
+                 accumulate: bool = False):
+        """accumulate=True (micro-batching, needs an attached reducer): the captured step is [forward, loss * loss_scale,
+        backward] only -- gradients accumulate in the reducer's bucket across calls; the caller zeroes the bucket, runs the
+        all-reduce and the optimizer once per optimizer step."""
         self.model, self.optimizer, self.reducer = model, optimizer, reducer
+        self.accumulate = bool(accumulate)
+        self.loss_scale = 1.0
+        assert not accumulate or (reducer is not None and optimizer is None)
         # collective_in_graph=False: the graph ends after the backward pass (gradients gathered in the flat bucket); the
         # all-reduce and the optimizer step are then issued eagerly after every replay
         self.split_tail = (not collective_in_graph) and reducer is not None and reducer.world > 1
@@ -163,14 +170,16 @@ class CapturedTrainStep(object):
 
     def _eager(self, s: _Slot, collective: bool = True):
         red = self.reducer
-        in_step = collective and not self.split_tail
+        in_step = collective and not self.split_tail and not self.accumulate
         if red is not None:
             red.overlap = in_step              # chunk all-reduces are issued from the backward pass
             # the local loss is a mean over the LOCAL claims: re-weight unequal shards
             red.set_weight(s.n_real * red.world / s.global_claims if (s.global_claims and red.world > 1) else 1.0)
         logits = self.model(s.query, s.document, **s.kw)
         loss = self.loss_fn(logits[:s.n_real], s.labels[:s.n_real])
-        loss.backward()
+        (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
+        if self.accumulate:
+            return logits, loss
         if red is not None:
             red.reduce(collective=in_step)
         if self.optimizer is not None and not self.split_tail:
@@ -211,14 +220,18 @@ class CapturedTrainStep(object):
             if hasattr(self.optimizer, "state_tensors"):        # get_b200.ddp.FlatAdam: flat moment buffers + device step
                 flat_backup = [t.detach().clone() for t in self.optimizer.state_tensors()]
         salt = ops.dropout_salt_get()
+        bucket_backup = self.reducer.flat.clone() if self.accumulate else None
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            self._zero_grad()
+            if not self.accumulate:
+                self._zero_grad()
             self._eager(s, collective=False)    # ranks see different shapes: building a graph must not be a collective
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        if bucket_backup is not None:
+            self.reducer.flat.copy_(bucket_backup)     # building a graph is not a step: gradients accumulated so far stay
         with torch.no_grad():
             for p, b in zip(params, backup):
                 p.copy_(b)
@@ -242,14 +255,15 @@ class CapturedTrainStep(object):
         ops.dropout_salt_set(salt)
         # ---- capture
         ops.prepare_split_table()      # host -> device copy of the weight-split job table: not allowed inside the capture
-        self._zero_grad()
+        if not self.accumulate:
+            self._zero_grad()
         prof, ops.PROFILE_GSL_EVENTS = ops.PROFILE_GSL_EVENTS, None
         g = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(g):
             ops.begin_step_capture()
             ops.dropout_salt_advance()
-            if self.reducer is not None and self.reducer.attached:
+            if self.reducer is not None and self.reducer.attached and not self.accumulate:
                 self.reducer.zero()        # part of the replayed step: gradients accumulate into the bucket
             s.logits, s.loss = self._eager(s)
         s.launches = _lib.launch_count() - n0      # kernels of libget_b200.so recorded in this graph

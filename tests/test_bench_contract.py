@@ -21,7 +21,11 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference modules when oracle/_ref (or /root/reference) is present, else the oracle port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_import
+    assert (d["cpu_baseline"]["kind"] == "reference") == ref_import.available()
+    assert set(d["config"].keys()) == {"workload", "step", "claims_per_gpu_per_step", "l2"}
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
 
