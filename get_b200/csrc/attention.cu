@@ -34,6 +34,7 @@ struct AttParams {
   __nv_bfloat16* du_p; int64_t ld_dup, ps_dup; int np_dup;   // du as bf16 planes (optional)
   int accumulate;
   int vec;              // H % 4 == 0, Dr % 4 == 0 and 16-byte aligned rows: 128-bit path
+  int dchunk;           // fwd: columns of `right` pooled per pass (bounds the partial-sum buffer)
 };
 
 // fwd smem: W2 (C*H) | att (P*C) | pooled partials (ATT_WARPS * Dr * C)   [the partials are reduced in a fixed order]
@@ -100,52 +101,58 @@ __global__ void __launch_bounds__(ATT_THREADS) att_pool_fwd_kernel(const __grid_
   }
   __syncthreads();
   // pooled[d,c] = sum_p right[p,d] * att[p,c]: warp w takes positions w, w+8, ...; lanes take column quads; the ATT_WARPS
-  // partial sums are reduced in a fixed order
+  // partial sums are reduced in a fixed order. Wide operands (evidence level: Dr = heads*H + E) go through the partial
+  // buffer in column chunks of p.dchunk.
   const float* rg = p.right + (int64_t)g * P * p.ld_right;
   float* og = p.pooled + (int64_t)g * p.ld_pooled;
-  if (p.vec) {
-    const int DQ = Dr >> 2;
-    for (int q0 = 0; q0 < DQ; q0 += 32) {
-      const int q = q0 + lane;
-      float acc[C][4];
+  const int DC = p.dchunk;
+  for (int d0 = 0; d0 < Dr; d0 += DC) {
+    const int dn = min(DC, Dr - d0);
+    if (p.vec) {
+      const int DQ = dn >> 2;
+      for (int q0 = 0; q0 < DQ; q0 += 32) {
+        const int q = q0 + lane;
+        float acc[C][4];
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
-      if (q < DQ) {
-        for (int pp = warp; pp < P; pp += ATT_WARPS) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(rg + (int64_t)pp * p.ld_right) + q);
+        for (int c = 0; c < C; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+        if (q < DQ) {
+          for (int pp = warp; pp < P; pp += ATT_WARPS) {
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(rg + (int64_t)pp * p.ld_right + d0) + q);
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float a = sE[pp * C + c];
-            acc[c][0] = fmaf(rv.x, a, acc[c][0]); acc[c][1] = fmaf(rv.y, a, acc[c][1]);
-            acc[c][2] = fmaf(rv.z, a, acc[c][2]); acc[c][3] = fmaf(rv.w, a, acc[c][3]);
+            for (int c = 0; c < C; ++c) {
+              const float a = sE[pp * C + c];
+              acc[c][0] = fmaf(rv.x, a, acc[c][0]); acc[c][1] = fmaf(rv.y, a, acc[c][1]);
+              acc[c][2] = fmaf(rv.z, a, acc[c][2]); acc[c][3] = fmaf(rv.w, a, acc[c][3]);
+            }
           }
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sPart[((size_t)warp * DC + q * 4 + e) * C + c] = acc[c][e];
+        }
+      }
+    } else {
+      for (int d = lane; d < dn; d += 32) {
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        for (int pp = warp; pp < P; pp += ATT_WARPS) {
+          const float rv = __ldg(rg + (int64_t)pp * p.ld_right + d0 + d);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(rv, sE[pp * C + c], acc[c]);
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) sPart[((size_t)warp * Dr + q * 4 + e) * C + c] = acc[c][e];
+        for (int c = 0; c < C; ++c) sPart[((size_t)warp * DC + d) * C + c] = acc[c];
       }
     }
-  } else {
-    for (int d = lane; d < Dr; d += 32) {
-      float acc[C];
+    __syncthreads();
+    for (int q = tid; q < dn * C; q += ATT_THREADS) {
+      float v = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = 0.f;
-      for (int pp = warp; pp < P; pp += ATT_WARPS) {
-        const float rv = __ldg(rg + (int64_t)pp * p.ld_right + d);
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fmaf(rv, sE[pp * C + c], acc[c]);
-      }
-#pragma unroll
-      for (int c = 0; c < C; ++c) sPart[((size_t)warp * Dr + d) * C + c] = acc[c];
+      for (int w = 0; w < ATT_WARPS; ++w) v += sPart[(size_t)w * DC * C + q];
+      og[(size_t)d0 * C + q] = v;
     }
-  }
-  __syncthreads();
-  for (int q = tid; q < Dr * C; q += ATT_THREADS) {
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < ATT_WARPS; ++w) v += sPart[(size_t)w * Dr * C + q];
-    og[q] = v;
+    __syncthreads();
   }
 }
 
@@ -363,7 +370,11 @@ extern "C" int get_att_pool_fwd_f32(const float* t, const float* right, int64_t 
   p.t = t; p.right = right; p.ld_right = ld_right; p.W2 = W2; p.mask = mask;
   p.G = G; p.P = P; p.H = H; p.Dr = Dr; p.C = C; p.att = att; p.pooled = pooled; p.ld_pooled = ld_pooled;
   p.vec = (H % 4) == 0 && (Dr % 4) == 0 && (ld_right % 4) == 0 && aligned16(t) && aligned16(right);
-  const size_t smem = ((size_t)C * H + (size_t)P * C + (size_t)ATT_WARPS * Dr * C) * sizeof(float);
+  int dchunk = (3072 / C) / 128 * 128;      // <= 96 KB of partial sums
+  if (dchunk < 128) dchunk = 128;
+  if (dchunk > Dr) dchunk = Dr;
+  p.dchunk = dchunk;
+  const size_t smem = ((size_t)C * H + (size_t)P * C + (size_t)ATT_WARPS * dchunk * C) * sizeof(float);
   return att_launch(att_fwd_fn(C), p, smem, (cudaStream_t)stream, "get_att_pool_fwd_f32");
 }
 

@@ -76,12 +76,22 @@ def gsl(adj: Tensor, score: Tensor, rate: float) -> Tensor:
 
 
 def ggnn_with_gsl(adj: Tensor, feat: Tensor, sd: SD, prefix: str, rate: float,
-                  drop_masks: Optional[Tuple[Tensor, Tensor, Tensor]] = None, return_parts: bool = False):
-    """`GGNN_with_GSL.forward` (wrapper.py:165-172). drop_masks = (feat_prop1, word_scorer1, feat_prop2)."""
+                  drop_masks: Optional[Tuple[Tensor, Tensor, Tensor]] = None, return_parts: bool = False,
+                  keep_override: Optional[Tuple[Tensor, Tensor]] = None):
+    """`GGNN_with_GSL.forward` (wrapper.py:165-172). drop_masks = (feat_prop1, word_scorer1, feat_prop2).
+
+    keep_override = (graphs (G,) bool, keep (G,N) bool): near-tie policy of the parity harness -- on
+    the listed graphs (those whose k-th score gap is below the fp32 re-association noise) the oracle follows the GIVEN
+    kept-node set instead of its own top-k, so that everything downstream can still be compared."""
     m1, ms, m2 = drop_masks if drop_masks is not None else (None, None, None)
     f1 = ggnn(adj, feat, sd, prefix + ".feat_prop1", m1)          # :166
     score = ggnn(adj, f1, sd, prefix + ".word_scorer1", ms)       # :167
     adj_refined = gsl(adj, score, rate)                           # :168
+    if keep_override is not None:
+        graphs, keep = keep_override
+        graphs, keep = graphs.to(adj.device), keep.to(adj.device)
+        forced = adj * (keep.unsqueeze(2) | keep.unsqueeze(1)).to(adj.dtype)
+        adj_refined = torch.where(graphs.view(-1, 1, 1), forced, adj_refined)
     f2 = ggnn(adj_refined, f1, sd, prefix + ".feat_prop2", m2)    # :169
     if return_parts:
         return f2, dict(f1=f1, score=score, keep_idx=gsl_topk(score, rate), adj_refined=adj_refined)
@@ -131,7 +141,8 @@ def pad_right(tsr: Tensor, evd_cnt: Tensor, max_num_evd: int) -> Tensor:
 
 
 def model_forward(sd: SD, cfg: dict, query: Tensor, document: Tensor, kargs: dict,
-                  drop_masks: Optional[dict] = None, dtype=torch.float32, return_parts: bool = False):
+                  drop_masks: Optional[dict] = None, dtype=torch.float32, return_parts: bool = False,
+                  keep_override: Optional[Tuple[Tensor, Tensor]] = None):
     """`Graph_basedSemantiStructure.forward` (Models/FCWithEvidences/graph_based_semantic_structure.py:76-125).
 
     cfg keys: gsl_rate, use_claim_source, use_article_source. drop_masks (train-mode parity) may hold
@@ -155,7 +166,8 @@ def model_forward(sd: SD, cfg: dict, query: Tensor, document: Tensor, kargs: dic
     # evidence graphs (:107)
     gm = (dm.get("feat_prop1"), dm.get("word_scorer1"), dm.get("feat_prop2"))
     doc_out, parts = ggnn_with_gsl(doc_adj, embed_doc, sd, "ggnn_with_gsl", cfg["gsl_rate"],
-                                   gm if any(m is not None for m in gm) else None, return_parts=True)
+                                   gm if any(m is not None for m in gm) else None, return_parts=True,
+                                   keep_override=keep_override)
     # word-level attention (:110, :173-193)
     avg, word_att = concat_not_equal_self_att(query_repr, doc_out, doc_mask,
                                               sd["self_att_word.linear1.weight"], sd["self_att_word.linear2.weight"])
@@ -195,7 +207,8 @@ def cross_entropy(logits: Tensor, labels: Tensor) -> Tensor:
 INERT_PREFIXES = ("bilstm.", "query_bilstm.", "trans.", "ggnn_with_gsl.word_scorer1.", "embedding.")
 
 
-def loss_and_grads(sd: SD, cfg: dict, query, document, labels, kargs, drop_masks=None, dtype=torch.float32):
+def loss_and_grads(sd: SD, cfg: dict, query, document, labels, kargs, drop_masks=None, dtype=torch.float32,
+                   keep_override=None):
     """Forward + autograd backward; returns (loss, logits, {name: grad}) for grad-receiving parameters."""
     leaves = {}
     for k, v in sd.items():
@@ -203,7 +216,7 @@ def loss_and_grads(sd: SD, cfg: dict, query, document, labels, kargs, drop_masks
         if v.is_floating_point() and not k.startswith(INERT_PREFIXES):
             v = v.clone().requires_grad_(True)
         leaves[k] = v
-    logits = model_forward(leaves, cfg, query, document, kargs, drop_masks, dtype)
+    logits = model_forward(leaves, cfg, query, document, kargs, drop_masks, dtype, keep_override=keep_override)
     loss = cross_entropy(logits, labels)
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if v.is_floating_point() and v.requires_grad and v.grad is not None}

@@ -214,7 +214,115 @@ def run_graph_cases():
     print("wrote graphs")
 
 
+def run_real_case(name="real_snopes", n_claims=6, D=100, H=100, seed=15):
+    """One mini-batch built from REAL rows of formatted_data/declare/Snopes (5fold/train_0.tsv) the way the reference's data
+    layer does it: whitespace tokens of the mapped text, the last 30 / 100 tokens (FixedLength truncate_mode='pre' keeps
+    the tail, matchzoo/preprocessors/units/fixed_length.py:24-30,63-64), word graphs by the reference's own
+    `ClassificationInteractions.convert_text` (interactions.py:334-351), article sources as ids, padding conventions of
+    handlers/mz_sampler.py:127-160. Real text brings what the synthetic generator does not: hub rows with dozens of
+    neighbours, the data's real pad fractions, a claim with >20 evidences. Stored: raw token ids (the test rebuilds the
+    batch and checks the graph restatement against the stored reference adjacency triplets) and the outputs / sampled
+    gradients of the unmodified reference model at reduced feature sizes (D = H = 100, heads 5/2)."""
+    import csv
+    import scipy.sparse as sp
+    import interactions as I
+
+    def lap(adj):
+        adj = sp.coo_matrix(adj)
+        rowsum = np.array(adj.sum(1))
+        with np.errstate(divide="ignore"):
+            d_inv_sqrt = np.power(rowsum, -0.5).flatten()
+        d_inv_sqrt[np.isinf(d_inv_sqrt)] = 0.
+        d = sp.diags(d_inv_sqrt)
+        return (adj.dot(d).transpose().dot(d)).toarray()
+    I._laplacian_normalize = lap
+    L, R, n = 30, 100, 30
+    path = os.path.join(_ref_root(), "formatted_data", "declare", "Snopes", "mapped_data", "5fold", "train_0.tsv")
+    claims = {}
+    with open(path, newline="") as fh:
+        for row in csv.DictReader(fh, delimiter="\t", quoting=csv.QUOTE_NONE):
+            c = claims.setdefault(row["id_left"], {"text": row["claim_text"], "label": row["cred_label"], "evd": []})
+            c["evd"].append((row["evidence"], row["evidence_source"]))
+    # the claim with the most evidences, one with a single evidence, and the next few in file order
+    by_cnt = sorted(claims.items(), key=lambda kv: -len(kv[1]["evd"]))
+    chosen = [by_cnt[0][0], by_cnt[-1][0]] + [k for k in list(claims)[:40] if k not in (by_cnt[0][0], by_cnt[-1][0])][:n_claims - 2]
+    vocab, sources = {"<PAD>": 0, "<OOV>": 1}, {}
+
+    def ids(text, keep):
+        toks = text.split()[-keep:]
+        return [vocab.setdefault(t, len(vocab)) for t in toks]
+    B = len(chosen)
+    cnt = np.array([min(n, len(claims[c]["evd"])) for c in chosen], np.int64)
+    B1 = int(cnt.sum())
+    batch = {"query": np.zeros((B, L), np.int64), K.Query_Adj: np.zeros((B, L, L)), K.Query_lens: np.zeros((B,), np.int64),
+             "document": np.zeros((B, n, R), np.int64), K.Doc_lens: np.zeros((B, n), np.int64),
+             K.DocSources: np.full((B, n), -1, np.int64), K.DocContentNoPaddingEvidence: np.zeros((B1, R), np.int64),
+             K.Evd_Docs_Adj: np.zeros((B1, R, R)), "e_lens": np.zeros((B1,), np.int64),
+             "raw_query_tokens": np.zeros((B, L), np.int64), "raw_query_lens": np.zeros((B,), np.int32),
+             "raw_doc_tokens": np.zeros((B1, R), np.int64), "raw_doc_lens": np.zeros((B1,), np.int32),
+             K.EvidenceCountPerQuery: cnt, K.FIXED_NUM_EVIDENCES: n, "window": 3,
+             K.QuerySources: np.zeros((B, 1), np.int64), "labels": np.zeros((B,), np.int64)}
+    g = 0
+    for b, cid in enumerate(chosen):
+        c = claims[cid]
+        toks = ids(c["text"], L)
+        nodes, adj, nn = I.ClassificationInteractions.convert_text(None, toks + [0] * (L - len(toks)), L, len(toks), 3)
+        batch["query"][b], batch[K.Query_Adj][b], batch[K.Query_lens][b] = nodes, adj, nn
+        batch["raw_query_tokens"][b, :len(toks)], batch["raw_query_lens"][b] = toks, len(toks)
+        batch["labels"][b] = 1 if c["label"].strip().lower() == "true" else 0
+        for j, (text, src) in enumerate(c["evd"][:n]):
+            toks = ids(text, R)
+            nodes, adj, nn = I.ClassificationInteractions.convert_text(None, toks + [0] * (R - len(toks)), R, len(toks), 3)
+            batch["document"][b, j], batch[K.Doc_lens][b, j] = nodes, nn
+            batch[K.DocSources][b, j] = sources.setdefault(src, len(sources))
+            batch[K.DocContentNoPaddingEvidence][g], batch[K.Evd_Docs_Adj][g], batch["e_lens"][g] = nodes, adj, nn
+            batch["raw_doc_tokens"][g, :len(toks)], batch["raw_doc_lens"][g] = toks, len(toks)
+            g += 1
+    batch["pairs"] = B1
+    w = synthetic.get_workload("snopes", name=name, batch_claims=B, vocab=len(vocab), emb_dim=D, hidden=H,
+                               n_article_sources=max(8, len(sources)))
+    model, params = build_reference_model(w, seed)
+    query, document, labels, kw = synthetic.batch_to_torch(batch)
+    kw[K.OutputRankingKey] = True
+    cap = {}
+    h = model.ggnn_with_gsl.word_scorer1.register_forward_hook(lambda m, i, o: cap.__setitem__("score", o.detach()))
+    logits, (word_att, evd_att) = model(query, document, **kw)
+    h.remove()
+    loss = torch.nn.CrossEntropyLoss()(logits, labels.long())
+    loss.backward()
+    out = {"cfg/seed": np.int64(seed), "cfg/dims": np.array([B, L, R, n, D, H, len(vocab), w.n_article_sources]),
+           "in/raw_query_tokens": batch["raw_query_tokens"], "in/raw_query_lens": batch["raw_query_lens"],
+           "in/raw_doc_tokens": batch["raw_doc_tokens"], "in/raw_doc_lens": batch["raw_doc_lens"],
+           "in/" + K.EvidenceCountPerQuery: cnt, "in/" + K.DocSources: batch[K.DocSources], "in/labels": batch["labels"],
+           "out/logits": logits.detach().numpy(), "out/loss": loss.detach().numpy(), "out/word_att": word_att.detach().numpy(),
+           "out/evd_att": evd_att.detach().numpy(), "out/score": cap["score"].numpy(),
+           "out/keep_idx": np.sort(cap["score"].topk(int(w.gsl_rate * R), 1)[1].squeeze(-1).numpy(), axis=1)}
+    # the reference adjacencies as sparse triplets (graph, row, col, value)
+    gi, ri, ci = np.nonzero(batch[K.Evd_Docs_Adj])
+    out["in/adj_idx"] = np.stack([gi, ri, ci]).astype(np.int16)
+    out["in/adj_val"] = batch[K.Evd_Docs_Adj][gi, ri, ci]
+    deg = (batch[K.Evd_Docs_Adj] != 0).sum(-1)
+    for nme, gr in ((n_, p.grad) for n_, p in model.named_parameters() if p.grad is not None):
+        gr = gr.detach()
+        out["gradsum/" + nme] = np.array([gr.double().sum().item(), gr.double().abs().sum().item()])
+        flat = gr.reshape(-1)
+        idx = np.random.default_rng([seed, zlib.crc32(nme.encode())]).integers(0, flat.numel(), size=min(64, flat.numel()))
+        out["gradidx/" + nme] = idx
+        out["gradval/" + nme] = flat[torch.from_numpy(idx)].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote %s: claims=%d pairs=%d evidences/claim=%s max neighbours per node=%d real nodes/graph=%.1f loss=%.6f" % (
+        name, B, B1, cnt.tolist(), int(deg.max()), float(batch["e_lens"].mean()), float(loss)))
+
+
+def _ref_root():
+    from _ref_import import REF_ROOT
+    return "/root/reference" if os.path.isdir("/root/reference/formatted_data") else REF_ROOT
+
+
 if __name__ == "__main__":
+    if "--real-only" in sys.argv:
+        run_real_case()
+        sys.exit(0)
     run_graph_cases()
     run_module_cases()
     run_model_case("tiny_snopes", synthetic.get_workload("tiny"), seed=11)
@@ -226,3 +334,4 @@ if __name__ == "__main__":
     run_model_case("snopes_dims", synthetic.get_workload("snopes", name="snopes_dims", batch_claims=3, vocab=400,
                                                          n_article_sources=16, evd_mean=2.5),
                    seed=14, store_sd=False, sample_only=True)
+    run_real_case()

@@ -50,3 +50,39 @@ def import_oracle():
 
 def keep_sets(idx) -> list:
     return [frozenset(int(i) for i in row) for row in np.asarray(idx)]
+
+
+def real_batch_from_golden(gold: dict):
+    """Rebuild the real-data mini-batch of tests/golden/real_snopes.npz from its raw token ids with the repo's restatement
+    of the reference's graph construction (get_b200.synthetic.word_graph), and check it against the stored triplets of the
+    adjacencies the REFERENCE's convert_text produced. Returns (workload, batch dict in the fitter's flattened layout)."""
+    from get_b200 import synthetic
+    from get_b200.keywords import KeyWordSettings as K
+    B, L, R, n, D, H, V, n_src = (int(x) for x in gold["cfg/dims"])
+    cnt = gold["in/" + K.EvidenceCountPerQuery].astype(np.int64)
+    B1 = int(cnt.sum())
+    w = synthetic.get_workload("snopes", name="real_snopes", batch_claims=B, vocab=V, emb_dim=D, hidden=H, n_article_sources=n_src)
+    batch = {"query": np.zeros((B, L), np.int64), K.Query_Adj: np.zeros((B, L, L)), K.Query_lens: np.zeros((B,), np.int64),
+             "document": np.zeros((B, n, R), np.int64), K.Doc_lens: np.zeros((B, n), np.int64),
+             K.DocSources: gold["in/" + K.DocSources].astype(np.int64), K.DocContentNoPaddingEvidence: np.zeros((B1, R), np.int64),
+             K.Evd_Docs_Adj: np.zeros((B1, R, R)), "e_lens": np.zeros((B1,), np.int64),
+             "raw_query_tokens": gold["in/raw_query_tokens"], "raw_query_lens": gold["in/raw_query_lens"],
+             "raw_doc_tokens": gold["in/raw_doc_tokens"], "raw_doc_lens": gold["in/raw_doc_lens"],
+             K.EvidenceCountPerQuery: cnt, K.FIXED_NUM_EVIDENCES: n, "window": 3,
+             K.QuerySources: np.zeros((B, 1), np.int64), "labels": gold["in/labels"].astype(np.int64), "pairs": B1}
+    g = 0
+    for b in range(B):
+        ql = int(gold["in/raw_query_lens"][b])
+        nodes, adj, nn = synthetic.word_graph(gold["in/raw_query_tokens"][b, :ql], L, 3)
+        batch["query"][b], batch[K.Query_Adj][b], batch[K.Query_lens][b] = nodes, adj, nn
+        for j in range(int(cnt[b])):
+            dl = int(gold["in/raw_doc_lens"][g])
+            nodes, adj, nn = synthetic.word_graph(gold["in/raw_doc_tokens"][g, :dl], R, 3)
+            batch["document"][b, j], batch[K.Doc_lens][b, j] = nodes, nn
+            batch[K.DocContentNoPaddingEvidence][g], batch[K.Evd_Docs_Adj][g], batch["e_lens"][g] = nodes, adj, nn
+            g += 1
+    ref_adj = np.zeros_like(batch[K.Evd_Docs_Adj])
+    gi, ri, ci = (gold["in/adj_idx"][i].astype(np.int64) for i in range(3))
+    ref_adj[gi, ri, ci] = gold["in/adj_val"]
+    assert np.array_equal(ref_adj, batch[K.Evd_Docs_Adj]), "graph restatement differs from the reference's convert_text on real text"
+    return w, batch

@@ -22,9 +22,9 @@ DEV = "cuda"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _setup(seed=123756, claims=32):
+def _setup(seed=123756, claims=32, workload="snopes", **over):
     from get_b200.model import Graph_basedSemantiStructure
-    w = synthetic.get_workload("snopes", batch_claims=claims)
+    w = synthetic.get_workload(workload, batch_claims=claims, **over)
     torch.manual_seed(seed)
     model = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=True)).to(DEV).eval()
     batch = synthetic.make_batch(w, seed=seed)
@@ -35,24 +35,36 @@ def _cfg(w):
     return dict(gsl_rate=w.gsl_rate, use_claim_source=w.use_claim_source, use_article_source=w.use_article_source)
 
 
-def test_full_size_parity_against_fp64_oracle_and_keep_sets():
+# (workload, claims, precision, tolerance): BASELINE.json configs[1] (Snopes, fp32 1e-4), configs[2] (PolitiFact: claim
+# source on, heads 3/1; fp32 1e-4 and bf16 1e-2 -- against the ORACLE, not against another mode of this code), and the
+# configs[3] shape (R=200, D=H=512, 8 word heads) at a batch the fp64 oracle handles
+CASES = [("snopes", 32, "fp32", 1e-4), ("politifact", 32, "fp32", 1e-4), ("politifact", 32, "bf16", 1e-2),
+         ("synthetic512", 3, "fp32", 1e-4), ("synthetic512", 3, "bf16", 1e-2)]
+
+
+@pytest.mark.parametrize("workload,claims,precision,tol", CASES)
+def test_full_size_parity_against_fp64_oracle_and_keep_sets(workload, claims, precision, tol):
     from get_b200 import ops
     from oracle import get_oracle as O
-    w, model, batch = _setup()
+    w, model, batch = _setup(workload=workload, claims=claims)
     q, d, l, kw = synthetic.batch_to_torch(batch, device=DEV)
     kw[K.OutputRankingKey] = True
-    logits, (word_att, evd_att) = model(q, d, **kw)
-    loss = ops.cross_entropy(logits, l)
-    loss.backward()
+    ops.set_precision(precision)
+    try:
+        logits, (word_att, evd_att) = model(q, d, **kw)
+        loss = ops.cross_entropy(logits, l)
+        loss.backward()
+    finally:
+        ops.set_precision("fp32")
     keep = model.ggnn_with_gsl.last_keep.bool().cpu()
     score = model.ggnn_with_gsl.last_score.cpu()
     sd64 = {k_: v.detach().double() for k_, v in model.state_dict().items()}
     kw64 = {k_: v for k_, v in kw.items() if k_ != K.OutputRankingKey}
-    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd64, _cfg(w), q, d, l, kw64, dtype=torch.float64)
     # kept sets from the oracle's own scores (fp64). Pad nodes share one score and have zero adjacency, so which pads are
     # "kept" is irrelevant: compare the REFINED ADJACENCIES (adj * (keep_i | keep_j)), the thing that reaches feat_prop2.
     _, parts = O.model_forward(sd64, _cfg(w), q, d, kw64, dtype=torch.float64, return_parts=True)
     ref_score = parts["score"].reshape(score.shape).cpu()
+    # the scorer chain is fp32-exact in EVERY precision mode
     assert float((score.double() - ref_score).abs().max()) < 1e-4
     kk = int(w.gsl_rate * w.len_right)
     ref_keep = torch.zeros_like(keep)
@@ -66,18 +78,23 @@ def test_full_size_parity_against_fp64_oracle_and_keep_sets():
     gap = (srt[:, kk - 1] - srt[:, kk]).abs()
     assert int((flipped & (gap >= 1e-5)).sum()) == 0, "refined adjacency differs on graphs with a clear k-th score gap"
     n_excused = int(flipped.sum())
-    print("graphs:", keep.shape[0], "near-tie graphs with a different kept node (excused, gap < 1e-5):", n_excused)
-    cnt = torch.as_tensor(batch[K.EvidenceCountPerQuery])
-    claim_of_graph = torch.repeat_interleave(torch.arange(cnt.shape[0]), cnt)
-    clean = torch.ones(cnt.shape[0], dtype=torch.bool)
-    clean[claim_of_graph[flipped]] = False
-    err = (logits.detach().double().cpu() - ref_logits.cpu()).abs()
-    assert float(err[clean].max()) < 1e-4
-    if n_excused == 0:
-        assert abs(float(loss) - float(ref_loss)) < 1e-4
-        for n, p in model.named_parameters():
-            if n in ref_grads and p.grad is not None:
-                assert float((p.grad.double() - ref_grads[n].to(DEV)).abs().max()) < 1e-4, n
+    print("graphs:", keep.shape[0], "near-tie graphs with a different kept node (gap < 1e-5):", n_excused)
+    # Near-tie policy: on those graphs the oracle follows OUR kept set, so that logits, loss and every
+    # gradient are checked on every claim in every run (nothing is skipped).
+    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd64, _cfg(w), q, d, l, kw64, dtype=torch.float64,
+                                                       keep_override=(flipped, keep) if n_excused else None)
+    scale = max(1.0, float(ref_logits.abs().max()))
+    assert float((logits.detach().double().cpu() - ref_logits.cpu()).abs().max()) < tol * scale
+    assert abs(float(loss) - float(ref_loss)) < tol
+    worst = ("", 0.0)
+    for n, p in model.named_parameters():
+        if n in ref_grads and p.grad is not None:
+            e = float((p.grad.double() - ref_grads[n].to(DEV)).abs().max())
+            gtol = tol * max(1.0, float(ref_grads[n].abs().max()))
+            assert e < gtol, (n, e, gtol)
+            worst = max(worst, (n, e), key=lambda t: t[1])
+    print("precision", precision, "tol", tol, "max |dlogits|", float((logits.detach().double().cpu() - ref_logits.cpu()).abs().max()),
+          "worst gradient", worst)
     # properties
     mask = (kw[K.DocContentNoPaddingEvidence] >= 1)
     assert float((word_att.sum(dim=1) - 1).abs().max()) < 1e-5

@@ -121,3 +121,33 @@ def test_word_graph_matches_reference_convert_text():
         assert np.array_equal(adj, g["g%d/adj" % i])
         i += 1
     assert i == 5
+
+
+def test_oracle_matches_reference_on_a_real_snopes_batch():
+    """Real TSV rows (formatted_data/declare/Snopes, 6 claims / 53 evidences, one claim with 28 evidences, hub nodes with up to
+    38 neighbours): the graph restatement equals the reference's convert_text, and the oracle equals the reference model."""
+    from helpers import named_param_values, real_batch_from_golden
+    from get_b200 import synthetic
+    from get_b200.keywords import KeyWordSettings as K
+    from get_b200.model import Graph_basedSemantiStructure
+    O = import_oracle()
+    gold = load_golden("real_snopes")
+    w, batch = real_batch_from_golden(gold)
+    assert int(batch[K.EvidenceCountPerQuery].max()) >= 20 and int((batch[K.Evd_Docs_Adj] != 0).sum(-1).max()) >= 30
+    seed = int(gold["cfg/seed"])
+    model = Graph_basedSemantiStructure(synthetic.match_params(w, seed=seed, cuda=False))
+    sd = model.state_dict()
+    vals = named_param_values({k: tuple(v.shape) for k, v in sd.items() if not k.endswith("embs.weight") and k != "embedding.weight"}, seed)
+    sd.update({k: torch.from_numpy(v) for k, v in vals.items()})
+    q, d, l, kw = synthetic.batch_to_torch(batch)
+    cfg = dict(gsl_rate=w.gsl_rate, use_claim_source=w.use_claim_source, use_article_source=w.use_article_source)
+    loss, logits, grads = O.loss_and_grads(sd, cfg, q, d, l, kw)
+    _, parts = O.model_forward(sd, cfg, q, d, kw, return_parts=True)
+    assert np.allclose(logits.numpy(), gold["out/logits"], atol=2e-6)
+    assert abs(float(loss) - float(gold["out/loss"])) < 2e-6
+    assert np.allclose(parts["word_att"].numpy(), gold["out/word_att"], atol=2e-6)
+    assert np.allclose(parts["evd_att"].numpy(), gold["out/evd_att"], atol=2e-6)
+    assert np.array_equal(np.sort(parts["keep_idx"].numpy(), axis=1), gold["out/keep_idx"])
+    for n, g in grads.items():
+        flat = g.reshape(-1)
+        assert np.allclose(flat[torch.from_numpy(gold["gradidx/" + n])].numpy(), gold["gradval/" + n], atol=2e-6), n
