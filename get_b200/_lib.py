@@ -56,6 +56,7 @@ class GemmBpDesc(C.Structure):
         ("drop_out_p", C.c_float), ("drop_out_seed", C.c_uint32),
         ("split_k", C.c_int32), ("kblock", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_floats", C.c_int64),
+        ("rowdot_w", C.c_void_p), ("rowdot_out", C.c_void_p), ("rowdot_p", C.c_float), ("rowdot_seed", C.c_uint32),
     ]
 
 
@@ -79,6 +80,7 @@ SIGNATURES = {
     "get_gemm_bp_tile_n": (_I, [_I, _I, _I]),
     "get_gemm_bp_ws_ld": (_L, [C.POINTER(GemmBpDesc)]),
     "get_gemm_bp_splits": (_I, [C.POINTER(GemmBpDesc)]),
+    "get_gemm_bp_rowdot_parts": (_I, [C.POINTER(GemmBpDesc)]),
     "get_bp_splitk_reduce": (_I, [_P, _I, _I, _L, C.POINTER(BpDst), _I, _I, _P]),
     "get_to_planes_bf16": (_I, [_P, _L, _I, _I, _P, _L, _L, _I, _I, _P]),
     "get_pack_planes_multi": (_I, [_P, _I, _L, _P]),
@@ -86,6 +88,9 @@ SIGNATURES = {
     "get_gsl_fused_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P]),
     "get_graph_aggregate_bp": (_I, [_P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
     "get_gsl_fused_bp": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "get_gsl_fused_sp": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _F, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "get_graph_split_slices": (_I, [_I, _I]),
+    "get_rowdot_f32": (_I, [_P, _P, _L, _I, _F, _U, _P, _P]),
     "get_gsl_mask_adj_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "get_att_pool_fwd_f32": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
     "get_att_pool_bwd_f32": (_I, [_P, _P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _I, _P]),

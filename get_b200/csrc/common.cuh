@@ -15,6 +15,11 @@ void count_launch(int n = 1);
 // per-step variation of the masks comes from this word, advanced by a one-thread kernel inside the graph.
 const uint32_t* dropout_salt_ptr();
 
+// TMA tensor map (CUtensorMap, 128 bytes) over {d0 inner contiguous, d1 rows `ld` elements apart[, d2 slices `ps` apart]} with
+// box {b0, b1[, b2]}; bf16 (f32 = 0) or fp32 elements; sw = swizzle span in bytes (0 = none). Memoised (gemm_bp.cu).
+bool make_tensor_map(void* map_out, const void* ptr, int f32, int rank, int64_t d0, int64_t d1, int64_t d2, int64_t ld, int64_t ps,
+                     int b0, int b1, int b2, int sw);
+
 #define GETB_REQUIRE(cond, ...)                 \
   do {                                          \
     if (!(cond)) {                              \

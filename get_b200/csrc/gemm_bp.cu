@@ -79,6 +79,10 @@ struct BpParams {
   int group_rows, zr_gs, zr_cols, zr_cols_pad;
   uint32_t drop_thr, drop_seed; float drop_scale;
   const uint32_t* salt;
+  // optional row-dot by-product of the TANH_BLEND epilogue (the scorer projection of the GSL block, wrapper.py:158,167):
+  // rd_out[(n_tile*2 + half)*M + m] = sum over this warp's columns of dropout_s(out[m,n]) * rd_w[n]
+  const float* rd_w; float* rd_out;
+  uint32_t rd_thr, rd_seed; float rd_scale;
 };
 
 __device__ __forceinline__ void bp_locate(const BpCfg& cfg, int kb, int& seg, int& kin) {
@@ -353,6 +357,7 @@ gemm_bp_kernel(const __grid_constant__ BpParams p, const __grid_constant__ BpCfg
         fence_before();
         mbar_arrive(&bar_acce[acc]);
       }
+      float rowdot = 0.f;
       for (int pc = chalf; pc < npieces; pc += 2) {
         const int col = pc << 4;
         const int n = n0 + col;
@@ -465,6 +470,19 @@ gemm_bp_kernel(const __grid_constant__ BpParams p, const __grid_constant__ BpCfg
           st_c = p.has_c && nv > 0;
           if (st_c) bp_stage_f32(stg_c, lane, w);
           st_p = p.has_pl;
+          if (p.rd_out) {
+            const uint32_t sd = p.rd_seed + (p.rd_thr ? __ldg(p.salt) : 0u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 4 < nv) {
+                const float4 rw = __ldg(reinterpret_cast<const float4*>(p.rd_w + n) + q);
+                float4 f = make_float4(w[q * 4 + 0], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
+                if (p.rd_thr) drop_apply4(sd, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + q * 4), p.rd_thr, p.rd_scale, f);
+                rowdot = fmaf(f.x, rw.x, rowdot); rowdot = fmaf(f.y, rw.y, rowdot);
+                rowdot = fmaf(f.z, rw.z, rowdot); rowdot = fmaf(f.w, rw.w, rowdot);
+              }
+            }
+          }
         } else if (EPI == GET_BPE_TANH_ROWGROUP) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) { v[e] = tanh_fast(v[e] + a0[e]); w[e] = v[e]; }
@@ -510,6 +528,7 @@ gemm_bp_kernel(const __grid_constant__ BpParams p, const __grid_constant__ BpCfg
           bulk_commit();
         }
       }
+      if (EPI == GET_BPE_TANH_BLEND && p.rd_out && row_ok && splits == 1) p.rd_out[(int64_t)(nt * 2 + chalf) * p.M + m] = rowdot;
       if (warp == 2 && lane == 0) BP_DBG(2, it * 2 + 1);
       if (acc_bufs == 2) {
         acc ^= 1;
@@ -669,10 +688,11 @@ struct BpMapKeyHash {
 };
 
 // Tensor map over {d0 inner contiguous, d1 rows `ld` elements apart[, d2 slices `ps` elements apart]}, box {b0, b1[, b2]};
-// elements bf16 (f32 = 0) or fp32 (f32 = 1); sw = swizzle span in bytes (32 / 64 / 128). Encoding is memoised: the
+// elements bf16 (f32 = 0) or fp32 (f32 = 1); sw = swizzle span in bytes (32 / 64 / 128, 0 = none). Encoding is memoised: the
 // allocator hands the same activation addresses back step after step.
-static bool bp_make_map(CUtensorMap* map, const void* ptr, int f32, int rank, int64_t d0, int64_t d1, int64_t d2, int64_t ld,
-                        int64_t ps, int b0, int b1, int b2, int sw) {
+bool make_tensor_map(void* map_out, const void* ptr, int f32, int rank, int64_t d0, int64_t d1, int64_t d2, int64_t ld,
+                     int64_t ps, int b0, int b1, int b2, int sw) {
+  CUtensorMap* map = reinterpret_cast<CUtensorMap*>(map_out);
   static std::mutex mu;
   static std::unordered_map<BpMapKey, CUtensorMap, BpMapKeyHash> cache;
   const BpMapKey key{ptr, d0, d1, d2, ld, ps, b0, b1, b2, sw, f32, rank};
@@ -692,7 +712,8 @@ static bool bp_make_map(CUtensorMap* map, const void* ptr, int f32, int rank, in
   cuuint64_t gstride[2] = {(cuuint64_t)ld * es, (cuuint64_t)(d2 > 1 ? ps : ld * d1) * es};
   cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  const CUtensorMapSwizzle swz = sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle swz = sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (sw == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   const CUresult rc = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
                           const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -780,6 +801,13 @@ static int bp_plan(const get_gemm_bp_desc* d, BpCfg& cfg, BpParams& p) {
   p.group_rows = d->group_rows; p.zr_gs = d->zr_group_stride; p.zr_cols = d->zr_cols;
   p.zr_cols_pad = bp_round_up(d->zr_cols, 8);
   p.salt = dropout_salt_ptr();
+  if (d->rowdot_out) {
+    GETB_REQUIRE(d->epilogue == GET_BPE_TANH_BLEND && d->rowdot_w && aligned16(d->rowdot_w) && d->rowdot_p >= 0.f && d->rowdot_p < 1.f,
+                 "get_gemm_bp: the row-dot by-product belongs to TANH_BLEND and needs a 16-byte aligned weight vector");
+    p.rd_w = d->rowdot_w; p.rd_out = d->rowdot_out;
+    p.rd_thr = d->rowdot_p > 0.f ? drop_threshold(d->rowdot_p) : 0u;
+    p.rd_seed = d->rowdot_seed; p.rd_scale = 1.0f / (1.0f - d->rowdot_p);
+  }
   {
     const int npl = p.has_pl ? p.nplanes : 0;
     int kb_set = d->epilogue == GET_BPE_ZR ? 2 + npl : 2 * p.has_c + 2 * p.has_o1 + npl;
@@ -902,24 +930,24 @@ static int bp_launch(const get_gemm_bp_desc* d, cudaStream_t st) {
   for (int s = 0; s < d->nseg; ++s) {
     const get_bp_tensor &A = d->A[s], &B = d->B[s];
     bool ok;
-    if (cfg.a_mn) ok = bp_make_map(&maps.a[s], A.ptr, 0, 3, d->M, d->K[s], np, A.ld, A.plane_stride, 64, kb, np, 128);
-    else ok = bp_make_map(&maps.a[s], A.ptr, 0, 3, d->K[s], d->M, np, A.ld, A.plane_stride, kb, BP_BM, np, kb == 64 ? 128 : 64);
+    if (cfg.a_mn) ok = make_tensor_map(&maps.a[s], A.ptr, 0, 3, d->M, d->K[s], np, A.ld, A.plane_stride, 64, kb, np, 128);
+    else ok = make_tensor_map(&maps.a[s], A.ptr, 0, 3, d->K[s], d->M, np, A.ld, A.plane_stride, kb, BP_BM, np, kb == 64 ? 128 : 64);
     if (!ok) return -3;
-    if (cfg.b_mn) ok = bp_make_map(&maps.b[s], B.ptr, 0, 3, d->N, d->K[s], np, B.ld, B.plane_stride, 64, kb, np, 128);
-    else ok = bp_make_map(&maps.b[s], B.ptr, 0, 3, d->K[s], d->N, np, B.ld, B.plane_stride, kb, cfg.BN, np, kb == 64 ? 128 : 64);
+    if (cfg.b_mn) ok = make_tensor_map(&maps.b[s], B.ptr, 0, 3, d->N, d->K[s], np, B.ld, B.plane_stride, 64, kb, np, 128);
+    else ok = make_tensor_map(&maps.b[s], B.ptr, 0, 3, d->K[s], d->N, np, B.ld, B.plane_stride, kb, cfg.BN, np, kb == 64 ? 128 : 64);
     if (!ok) return -3;
   }
   // output maps: the epilogue leaves through TMA stores of 32-row x 16-column pieces (clipped at the tensor edges)
   const bool zr = d->epilogue == GET_BPE_ZR;
   if (cfg.splits > 1) {
     const int64_t ws_ld = (int64_t)cfg.ntn * cfg.BN;
-    if (!bp_make_map(&maps.c, d->workspace, 1, 3, ws_ld, d->M, cfg.splits, ws_ld, (int64_t)d->M * ws_ld, 16, 32, 1, 64)) return -3;
+    if (!make_tensor_map(&maps.c, d->workspace, 1, 3, ws_ld, d->M, cfg.splits, ws_ld, (int64_t)d->M * ws_ld, 16, 32, 1, 64)) return -3;
   } else {
     const int64_t ncols = zr ? d->zr_cols : d->N;
-    if (d->C && !bp_make_map(&maps.c, d->C, 1, 2, ncols, d->M, 1, d->ldc, 0, 16, 32, 1, 64)) return -3;
-    if (d->out1 && !bp_make_map(&maps.o1, d->out1, 1, 2, ncols, d->M, 1, d->ld_out1, 0, 16, 32, 1, 64)) return -3;
+    if (d->C && !make_tensor_map(&maps.c, d->C, 1, 2, ncols, d->M, 1, d->ldc, 0, 16, 32, 1, 64)) return -3;
+    if (d->out1 && !make_tensor_map(&maps.o1, d->out1, 1, 2, ncols, d->M, 1, d->ld_out1, 0, 16, 32, 1, 64)) return -3;
     if (d->planes_out &&
-        !bp_make_map(&maps.pl, d->planes_out, 0, 3, zr ? p.zr_cols_pad : p.Npad, d->M, d->planes_out_n, d->ld_planes_out,
+        !make_tensor_map(&maps.pl, d->planes_out, 0, 3, zr ? p.zr_cols_pad : p.Npad, d->M, d->planes_out_n, d->ld_planes_out,
                      d->planes_out_stride, 16, 32, 1, 32))
       return -3;
   }
@@ -983,6 +1011,17 @@ extern "C" int get_gemm_bp_splits(const get_gemm_bp_desc* desc) {
   d.workspace_floats = INT64_MAX;
   if (bp_plan(&d, cfg, p) != 0) return -1;
   return cfg.splits;
+}
+
+extern "C" int get_gemm_bp_rowdot_parts(const get_gemm_bp_desc* desc) {
+  BpCfg cfg;
+  BpParams p;
+  get_gemm_bp_desc d = *desc;
+  d.workspace = reinterpret_cast<float*>(16);
+  d.workspace_floats = INT64_MAX;
+  d.rowdot_out = nullptr;
+  if (bp_plan(&d, cfg, p) != 0) return -1;
+  return 2 * cfg.ntn;
 }
 
 extern "C" int get_bp_splitk_reduce(const float* workspace, int splits, int M, int64_t ws_ld, const get_bp_dst* dsts, int ndst,

@@ -517,95 +517,95 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
 }
 
 // =====================================================================================================
-// Cluster path (experimental, opt-in): one graph per 2-CTA thread-block cluster, each CTA owns half of the feature
-// columns. Two such CTAs (~103 KB of shared memory, 512 threads) are co-resident per SM, so one CTA's TMA loads overlap
-// the other's compute, and a 216-graph launch becomes 432 half-size work items instead of two partial waves.
-// The only cross-CTA data are the N partial scorer dot products, exchanged through distributed shared memory.
-// Measured on B200: 37 us vs 35 us at 216 graphs and 928 us vs 566 us at 7 680 graphs -- the duplicated list building /
-// top-k and the 38-of-64 lane utilisation of the half rows cost more than the overlap buys, so it is not the default.
+// Column-split path (the default fast path): one graph = `nsplit` INDEPENDENT 512-thread CTAs, each owning a slice of the
+// feature columns (aggregation is independent per column once the kept-node set is known). A slice of a Snopes graph is
+// 61 KB of features + the 40 KB adjacency, so TWO CTAs are co-resident per SM: one CTA's TMA loads and row stores overlap
+// the other's compute, and a 216-graph launch becomes 432 work items instead of two partial waves of whole graphs.
+// What makes the slices independent is that the scorer's projection s_p = dropout_s(F) . w_p (the only quantity that needs
+// whole feature rows) arrives precomputed: it is a by-product of the epilogue of the GEMM that wrote F (get_gemm_bp,
+// rowdot_out), or of a small row-dot kernel for the stand-alone entry points. Every CTA recomputes the cheap per-graph
+// part (neighbour lists, SpMV of the scorer, scalar GRU gates, top-k) from the adjacency it has to load anyway.
+//   * adjacency: one bulk copy; features: ONE 2-D TMA box {slice columns, N rows} (tensor map over (G*N, H));
+//   * neighbour lists built in place over the dense tile (rows with more than N/2 neighbours stay dense);
+//   * aggregation: half a warp per output row (a 38-quad slice keeps 38 of 48 lane slots busy), 128-bit shared loads,
+//     results leave as fp32 rows and / or bf16 planes for the next tensor-core contraction.
 // =====================================================================================================
-constexpr int GC_THREADS = 512;
-constexpr int GC_WARPS = GC_THREADS / 32;
-constexpr int GC_ROWS_PER_WARP = GS_MAX_N / GC_WARPS;   // 8
+constexpr int GP_THREADS = 512;
+constexpr int GP_WARPS = GP_THREADS / 32;
+constexpr int GP_ROWS_PER_WARP = GS_MAX_N / GP_WARPS;   // 8
+constexpr size_t GP_SMEM_PER_CTA = 112 * 1024;          // two CTAs per SM
 
-__device__ __forceinline__ uint32_t gc_cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void gc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void gc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ float gc_ld_peer(const float* local_ptr, uint32_t peer) {
-  uint32_t raddr;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(gs_smem_u32(local_ptr)), "r"(peer));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
-  return v;
+struct SplitParams {
+  GraphParams g;
+  const float* sp_parts;   // (n_sp, G*N) partial scorer projections, summed in order
+  int n_sp;
+  int nsplit, qs;          // column slices per graph; float4 quads per slice
+};
+
+__device__ __forceinline__ void gp_tma_load_2d(void* dst, const void* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(gs_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(gs_smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
 }
 
-// smem: [F N*WP f32 (own columns, row pitch WP)] [adj N*N f32 -> per-row lists in place, N/2 entries of 8 B per row]
-//       [part N] [sp N] [score N] [cnt N i32] [rank N i32] [keep N u8] [mbarriers 1 + GS_CHUNKS]
-template <bool FUSED>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GC_THREADS, 2) graph_cluster_kernel(const __grid_constant__ GraphParams p) {
-  extern __shared__ __align__(16) float smem[];
-  const int g = blockIdx.x >> 1;
-  const uint32_t crank = gc_cluster_rank();
+struct alignas(64) TmapBytes { unsigned char b[128]; };
+
+// smem: [F slice N*WP f32 (row pitch WP = qs*4)] [adj N*N f32 -> per-row lists in place, N/2 entries of 8 B per row]
+//       [sp N] [score N] [cnt N i32] [rank N i32] [keep N u8] [mbarriers 2]
+template <bool FUSED, int NQH>
+__global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid_constant__ SplitParams sp, const __grid_constant__ TmapBytes fmap) {
+  extern __shared__ __align__(128) float smem[];
+  const GraphParams& p = sp.g;
+  const int g = blockIdx.x / sp.nsplit, slice = blockIdx.x - g * sp.nsplit;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, H = p.H, HQ = H >> 2;
-  const int qsplit = (HQ + 1) >> 1;                 // quads of rank 0; rank 1 owns the rest
-  const int q0 = crank ? qsplit : 0;                // first global quad of this CTA
-  const int WQ = crank ? HQ - qsplit : qsplit;      // quads owned
-  const int WP = qsplit * 4;                        // smem row pitch in floats (same for both ranks)
+  const int q0 = slice * sp.qs;                        // first global quad of this CTA
+  const int WQ = min(sp.qs, HQ - q0);                  // quads owned
+  const int WP = sp.qs * 4;                            // smem row pitch in floats
   const uint32_t salt = (FUSED && p.thr) ? __ldg(p.salt) : 0u;
-  const uint32_t seed_s = p.seed_s + salt, seed_2 = p.seed_2 + salt;
+  const uint32_t seed_2 = p.seed_2 + salt;
 
   float* sF = smem;
   float* sA = sF + (size_t)N * WP;
-  float* s_part = sA + (size_t)N * N;
-  float* s_sp = s_part + N;
+  float* s_sp = sA + (size_t)N * N;
   float* s_score = s_sp + N;
   int* s_cnt = reinterpret_cast<int*>(s_score + N);
   int* s_rank = s_cnt + N;
   uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_rank + N);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_keep + ((N + 15) & ~15));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_keep + ((N + 15) & ~15));   // [0] adjacency, [1] features
 
   const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
-  const float* __restrict__ gx = p.x + (int64_t)g * N * H + (int64_t)q0 * 4;
-  float* __restrict__ gout = p.out + (int64_t)g * N * H + (int64_t)q0 * 4;
-  const int nchunks = (N + 31) >> 5;
-  const bool own0 = lane < WQ, own1 = lane + 32 < WQ;   // this lane's (up to two) quads of a row
-
   if (tid == 0) {
-    for (int b = 0; b <= GS_CHUNKS; ++b) gs_mbar_init(&bars[b], 1);
+    gs_mbar_init(&bars[0], 1);
+    gs_mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t abytes = (uint32_t)N * (uint32_t)N * 4u;
-      gs_mbar_expect_tx(&bars[0], abytes);
-      gs_bulk_g2s(sA, gadj, abytes, &bars[0]);
-    }
-    const uint32_t rowbytes = (uint32_t)WQ * 16u;
-    for (int c = 0; c < nchunks; ++c) {
-      const int r0 = c * 32, nr = min(N, r0 + 32) - r0;
-      if (lane == 0) gs_mbar_expect_tx(&bars[1 + c], (uint32_t)nr * rowbytes);
-      __syncwarp();
-      if (lane < nr) gs_bulk_g2s(sF + (size_t)(r0 + lane) * WP, gx + (size_t)(r0 + lane) * H, rowbytes, &bars[1 + c]);
-    }
+  if (tid == 0) {
+    const uint32_t abytes = (uint32_t)N * (uint32_t)N * 4u;
+    gs_mbar_expect_tx(&bars[0], abytes);
+    gs_bulk_g2s(sA, gadj, abytes, &bars[0]);
+    gs_mbar_expect_tx(&bars[1], (uint32_t)N * (uint32_t)WP * 4u);
+    gp_tma_load_2d(sF, &fmap, q0 * 4, g * N, &bars[1]);
   }
   if (tid < N) {
     s_rank[tid] = 0;
     if (!FUSED) s_keep[tid] = p.keep_in ? p.keep_in[(int64_t)g * N + tid] : (uint8_t)1;
+    if (FUSED) {
+      float v = 0.f;
+      for (int q = 0; q < sp.n_sp; ++q) v += __ldg(sp.sp_parts + (int64_t)q * p.G * N + (int64_t)g * N + tid);   // fixed order
+      s_sp[tid] = v;
+    }
   }
 
   // ---- neighbour lists in place: row i -> {byte offset of F row j, w_ij}; rows with more than N/2 neighbours stay dense
   gs_mbar_wait(&bars[0], 0);
   {
-    float wv[GC_ROWS_PER_WARP][4];
+    float wv[GP_ROWS_PER_WARP][4];
 #pragma unroll
-    for (int r = 0; r < GC_ROWS_PER_WARP; ++r) {
-      const int i = warp + r * GC_WARPS;
+    for (int r = 0; r < GP_ROWS_PER_WARP; ++r) {
+      const int i = warp + r * GP_WARPS;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int j = c * 32 + lane;
@@ -614,8 +614,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GC_THREADS, 2) graph
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < GC_ROWS_PER_WARP; ++r) {
-      const int i = warp + r * GC_WARPS;
+    for (int r = 0; r < GP_ROWS_PER_WARP; ++r) {
+      const int i = warp + r * GP_WARPS;
       if (i < N) {
         unsigned nz[4];
         int total = 0;
@@ -645,51 +645,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GC_THREADS, 2) graph
       }
     }
   }
+  __syncthreads();
 
+  const float inv_rowbytes = 1.0f / (float)(WP * 4);   // offsets are exact multiples of WP*4 < 2^24: rounding recovers j
   if (FUSED) {
-    // ---- partial s_p over the own columns; layer-2 dropout applied in place on the way -------------------------
-    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-    if (own0) w0 = __ldg(reinterpret_cast<const float4*>(p.wp) + q0 + lane);
-    if (own1) w1 = __ldg(reinterpret_cast<const float4*>(p.wp) + q0 + lane + 32);
-    for (int c = 0; c < nchunks; ++c) {
-      gs_mbar_wait(&bars[1 + c], 0);
-      for (int i = c * 32 + warp; i < min(N, c * 32 + 32); i += GC_WARPS) {
-        float4* row = reinterpret_cast<float4*>(sF + (size_t)i * WP) + lane;
-        float acc = 0.f;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (u == 0 ? own0 : own1) {
-            float4 f = row[u * 32];
-            if (p.thr) {
-              const uint64_t base = ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)(q0 + lane + u * 32) * 4;
-              float4 f2 = f;
-              drop_apply4(seed_2, base, p.thr, p.scale, f2);
-              row[u * 32] = f2;
-              drop_apply4(seed_s, base, p.thr, p.scale, f);
-            }
-            const float4 w = u == 0 ? w0 : w1;
-            acc = fmaf(f.x, w.x, acc); acc = fmaf(f.y, w.y, acc);
-            acc = fmaf(f.z, w.z, acc); acc = fmaf(f.w, w.w, acc);
-          }
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) s_part[i] = acc;
-      }
-    }
-    __syncthreads();
-    gc_cluster_arrive();
-    gc_cluster_wait();                      // both halves of every dot product are in place
-    if (tid < N) {
-      const float mine = s_part[tid], peer = gc_ld_peer(&s_part[tid], crank ^ 1u);
-      s_sp[tid] = crank ? peer + mine : mine + peer;      // rank-0 half first in both CTAs: identical bits
-    }
-    gc_cluster_arrive();                    // (second phase) waited for at the very end: the peer may still be reading
-    __syncthreads();
-    // ---- s_a = adj @ s_p + scalar GRU gates (GGNN with out_features = 1), one thread per node ----------------
+    // ---- s_a = adj @ s_p + scalar GRU gates (GGNN with out_features = 1), one thread per node -------------------
     if (tid < N) {
       const int i = tid;
       const int cnt = s_cnt[i];
-      const float inv_rowbytes = 1.0f / (float)(WP * 4);
       float sa = 0.f;
       if (cnt >= 0) {
         const float2* lr = reinterpret_cast<const float2*>(sA + (size_t)i * N);
@@ -703,18 +666,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GC_THREADS, 2) graph
       const float wz0 = __ldg(p.gate + 0), bz0 = __ldg(p.gate + 1), wz1 = __ldg(p.gate + 2), bz1 = __ldg(p.gate + 3);
       const float wr0 = __ldg(p.gate + 4), br0 = __ldg(p.gate + 5), wr1 = __ldg(p.gate + 6), br1 = __ldg(p.gate + 7);
       const float wh0 = __ldg(p.gate + 8), bh0 = __ldg(p.gate + 9), wh1 = __ldg(p.gate + 10), bh1 = __ldg(p.gate + 11);
-      const float sp = s_sp[i];
-      const float z = sigmoidf_((wz0 * sa + bz0) + (wz1 * sp + bz1));
-      const float r = sigmoidf_((wr0 * sa + br0) + (wr1 * sp + br1));
-      const float h = tanhf((wh0 * sa + bh0) + (wh1 * (r * sp) + bh1));
-      const float sc = h * z + sp * (1.0f - z);
+      const float spv = s_sp[i];
+      const float z = sigmoidf_((wz0 * sa + bz0) + (wz1 * spv + bz1));
+      const float r = sigmoidf_((wr0 * sa + br0) + (wr1 * spv + br1));
+      const float h = tanhf((wh0 * sa + bh0) + (wh1 * (r * spv) + bh1));
+      const float sc = h * z + spv * (1.0f - z);
       s_score[i] = sc;
-      if (p.score && crank == 0) p.score[(int64_t)g * N + i] = sc;
+      if (p.score && slice == 0) p.score[(int64_t)g * N + i] = sc;
     }
     __syncthreads();
+    // ---- top-k by rank counting: thread (node i, slice of 32 candidates); ties -> lower index first -------------
     {
       const int i = tid & (GS_MAX_N - 1);
-      const int j0 = (tid >> 7) * 32;         // 4 slices of 32 candidates
+      const int j0 = (tid >> 7) * 32;
       if (i < N && j0 < N) {
         const float si = s_score[i];
         const int j1 = min(N, j0 + 32);
@@ -730,71 +694,136 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GC_THREADS, 2) graph
     if (tid < N) {
       const uint8_t kp = s_rank[tid] < p.k;
       s_keep[tid] = kp;
-      if (crank == 0) p.keep_out[(int64_t)g * N + tid] = kp;
+      if (slice == 0) p.keep_out[(int64_t)g * N + tid] = kp;
     }
-    __syncthreads();
-  } else {
-    for (int c = 0; c < nchunks; ++c) gs_mbar_wait(&bars[1 + c], 0);
-    __syncthreads();
   }
 
-  // ---- out[i, own columns] = sum_e w[i][e] * x[idx[i][e], own columns] -----------------------------------------
+  // ---- features have landed: the layer-2 dropout draw is applied in place -----------------------------------------
+  gs_mbar_wait(&bars[1], 0);
+  if (FUSED && p.thr) {
+    for (int e = tid; e < N * WQ; e += GP_THREADS) {
+      const int i = e / WQ, q = e - i * WQ;
+      float4* f = reinterpret_cast<float4*>(sF + (size_t)i * WP) + q;
+      float4 v = *f;
+      drop_apply4(seed_2, ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)(q0 + q) * 4, p.thr, p.scale, v);
+      *f = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- out[i, own columns] = sum_e w[i][e] * x[idx[i][e], own columns]; half a warp per row ------------------------
   const bool masked = FUSED || (p.keep_in != nullptr);
-  const char* sFb = reinterpret_cast<const char*>(sF) + lane * 16;
-  const float inv_rowbytes = 1.0f / (float)(WP * 4);
-  for (int i = warp; i < N; i += GC_WARPS) {
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  const int hw = lane >> 4, hl = lane & 15;
+  const char* sFb = reinterpret_cast<const char*>(sF) + hl * 16;
+  const bool last_slice = slice == sp.nsplit - 1;
+  const int npq = last_slice ? ((((H + (p.pad_one ? 1 : 0)) + 7) & ~7) - H) >> 2 : 0;     // padding quads of the plane rows
+  for (int i = warp * 2 + hw; i < N; i += 2 * GP_WARPS) {
+    float4 acc[NQH];
+#pragma unroll
+    for (int u = 0; u < NQH; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int cnt = s_cnt[i];
-    const bool dropped = masked && s_keep[i] == 0;   // a dropped node keeps only its edges to kept nodes
+    const bool dropped = masked && s_keep[i] == 0;   // a dropped node keeps only its edges to kept nodes (wrapper.py:221-225)
     if (cnt >= 0) {
-      float2* lr = reinterpret_cast<float2*>(sA + (size_t)i * N);
-      if (dropped) {
-        for (int e = lane; e < cnt; e += 32) {
-          const int j = __float2int_rn(__int2float_rn(__float_as_int(lr[e].x)) * inv_rowbytes);
-          if (!s_keep[j]) lr[e].y = 0.f;
-        }
-        __syncwarp();
-      }
+      const float2* lr = reinterpret_cast<const float2*>(sA + (size_t)i * N);
 #pragma unroll 2
       for (int e = 0; e < cnt; ++e) {
         const float2 en = lr[e];
-        const float wj = en.y;
-        const float4* row = reinterpret_cast<const float4*>(sFb + __float_as_int(en.x));
-        if (own0) {
-          const float4 f = row[0];
-          a0.x = fmaf(wj, f.x, a0.x); a0.y = fmaf(wj, f.y, a0.y); a0.z = fmaf(wj, f.z, a0.z); a0.w = fmaf(wj, f.w, a0.w);
-        }
-        if (own1) {
-          const float4 f = row[32];
-          a1.x = fmaf(wj, f.x, a1.x); a1.y = fmaf(wj, f.y, a1.y); a1.z = fmaf(wj, f.z, a1.z); a1.w = fmaf(wj, f.w, a1.w);
+        float wj = en.y;
+        const int off = __float_as_int(en.x);
+        if (dropped && !s_keep[__float2int_rn(__int2float_rn(off) * inv_rowbytes)]) wj = 0.f;
+        const float4* row = reinterpret_cast<const float4*>(sFb + off);
+#pragma unroll
+        for (int u = 0; u < NQH; ++u) {
+          if (hl + u * 16 < WQ) {
+            const float4 f = row[u * 16];
+            acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
+            acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
+          }
         }
       }
     } else {
       for (int j = 0; j < N; ++j) {               // dense row (more than N/2 neighbours)
-        float wj = sA[(size_t)i * N + j];
+        const float wj = sA[(size_t)i * N + j];
         if (wj == 0.f || (dropped && !s_keep[j])) continue;
         const float4* row = reinterpret_cast<const float4*>(sFb + (size_t)j * WP * 4);
-        if (own0) {
-          const float4 f = row[0];
-          a0.x = fmaf(wj, f.x, a0.x); a0.y = fmaf(wj, f.y, a0.y); a0.z = fmaf(wj, f.z, a0.z); a0.w = fmaf(wj, f.w, a0.w);
-        }
-        if (own1) {
-          const float4 f = row[32];
-          a1.x = fmaf(wj, f.x, a1.x); a1.y = fmaf(wj, f.y, a1.y); a1.z = fmaf(wj, f.z, a1.z); a1.w = fmaf(wj, f.w, a1.w);
+#pragma unroll
+        for (int u = 0; u < NQH; ++u) {
+          if (hl + u * 16 < WQ) {
+            const float4 f = row[u * 16];
+            acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
+            acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
+          }
         }
       }
     }
-    float4* orow = reinterpret_cast<float4*>(gout + (int64_t)i * H) + lane;
-    if (own0) {
-      if (p.accumulate) { const float4 o = orow[0]; a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w; }
-      orow[0] = a0;
+    float* orow = p.out ? p.out + ((int64_t)g * N + i) * H + (int64_t)q0 * 4 : nullptr;
+    __nv_bfloat16* prow = p.out_p ? p.out_p + ((int64_t)g * N + i) * p.ld_p + (int64_t)q0 * 4 : nullptr;
+#pragma unroll
+    for (int u = 0; u < NQH; ++u) {
+      const int q = hl + u * 16;
+      if (q < WQ) {
+        float4 v = acc[u];
+        if (p.accumulate) {
+          const float4 o = *(reinterpret_cast<const float4*>(orow) + q);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        if (orow) *(reinterpret_cast<float4*>(orow) + q) = v;
+        if (prow) {
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          planes_store4(prow + q * 4, p.ps_p, p.np_p, vv);
+        }
+      }
     }
-    if (own1) {
-      if (p.accumulate) { const float4 o = orow[32]; a1.x += o.x; a1.y += o.y; a1.z += o.z; a1.w += o.w; }
-      orow[32] = a1;
+    if (prow && hl < npq) {     // padding quads up to a multiple of 8 columns (room for the ones column when pad_one)
+      const float vv[4] = {(p.pad_one && hl == 0) ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
+      planes_store4(p.out_p + ((int64_t)g * N + i) * p.ld_p + H + hl * 4, p.ps_p, p.np_p, vv);
     }
   }
-  if (FUSED) gc_cluster_wait();   // the peer has finished reading this CTA's partial scores
+}
+
+// s_p[m] = dropout_s(F[m,:]) . wp  -- the scorer projection for the stand-alone entry points (in the model it is a by-product
+// of the epilogue of the GEMM that writes F); one warp per row
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ F, const float* __restrict__ wp, int64_t M, int H,
+                                                     uint32_t thr, float scale, uint32_t seed, const uint32_t* __restrict__ salt,
+                                                     float* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sd = seed + (thr ? __ldg(salt) : 0u);
+  float acc = 0.f;
+  for (int q = lane; q < (H >> 2); q += 32) {
+    float4 f = __ldg(reinterpret_cast<const float4*>(F + m * H) + q);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wp) + q);
+    if (thr) drop_apply4(sd, (uint64_t)m * (uint64_t)H + (uint64_t)q * 4, thr, scale, f);
+    acc = fmaf(f.x, w.x, acc); acc = fmaf(f.y, w.y, acc); acc = fmaf(f.z, w.z, acc); acc = fmaf(f.w, w.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[m] = acc;
+}
+
+typedef void (*GraphSplitFn)(const SplitParams, const TmapBytes);
+static GraphSplitFn graph_split_fn(bool fused, int nqh) {
+  switch (nqh) {
+    case 1: return fused ? graph_split_kernel<true, 1> : graph_split_kernel<false, 1>;
+    case 2: return fused ? graph_split_kernel<true, 2> : graph_split_kernel<false, 2>;
+    case 3: return fused ? graph_split_kernel<true, 3> : graph_split_kernel<false, 3>;
+    default: return fused ? graph_split_kernel<true, 4> : graph_split_kernel<false, 4>;
+  }
+}
+
+// plan of the column-split path: smallest number of slices whose CTA fits twice per SM; 0 = not applicable
+static int graph_split_plan(const GraphParams& p, bool fused, int& qs, size_t& smem) {
+  if ((p.H % 4) != 0 || (p.N % 2) != 0 || p.N > GS_MAX_N || !aligned16(p.adj) || !aligned16(p.x) || (p.out && !aligned16(p.out)))
+    return 0;
+  const int hq = p.H / 4;
+  for (int s = 1; s <= 8; ++s) {
+    qs = (hq + s - 1) / s;
+    if (qs > 64 || (s - 1) * qs >= hq) continue;
+    smem = ((size_t)p.N * qs * 4 + (size_t)p.N * p.N + 4 * (size_t)p.N) * sizeof(float) + (((size_t)p.N + 15) & ~(size_t)15) +
+           2 * sizeof(uint64_t) + 128;
+    if (smem <= GP_SMEM_PER_CTA) return s;
+  }
+  return 0;
 }
 
 typedef void (*GraphSmemFn)(const GraphParams);
@@ -836,7 +865,8 @@ __global__ void __launch_bounds__(GRAPH_THREADS) gsl_mask_adj_kernel(const float
   }
 }
 
-static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char* name) {
+static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char* name, const float* sp_parts = nullptr,
+                        int n_sp = 0) {
   GETB_REQUIRE(p.G >= 0 && p.N > 0 && p.H > 0, "%s: bad sizes G=%d N=%d H=%d", name, p.G, p.N, p.H);
   GETB_REQUIRE(p.H <= 32 * 4 * MAX_QUADS_PER_LANE, "%s: H=%d exceeds %d", name, p.H, 32 * 4 * MAX_QUADS_PER_LANE);
   GETB_REQUIRE(p.out || p.out_p, "%s: no output", name);
@@ -847,33 +877,38 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
                  "%s: plane output needs H %% 4 == 0 and aligned tensors", name);
   if (p.G == 0) return 0;
   {
-    // experimental path (GET_B200_GRAPH_CLUSTER=1): 2-CTA cluster per graph, feature columns split between the CTAs
-    const int hq = p.H / 4, wp = ((hq + 1) / 2) * 4;
-    const size_t need_c = ((size_t)p.N * wp + (size_t)p.N * p.N + 5 * (size_t)p.N) * sizeof(float) +
-                          (((size_t)p.N + 15) & ~(size_t)15) + (GS_CHUNKS + 1) * sizeof(uint64_t);
-    static int use_cluster = -1;
-    if (use_cluster < 0) {
-      const char* e = getenv("GET_B200_GRAPH_CLUSTER");
-      use_cluster = e ? atoi(e) : 0;   // measured slower than the single-CTA path on B200 (profiles/): opt-in only
+    // column-split path: `nsplit` independent CTAs per graph, two co-resident per SM. The fused kernel needs the scorer
+    // projection precomputed (sp_parts); the plain aggregation needs nothing extra.
+    static int use_split = -1;
+    if (use_split < 0) {
+      const char* e = getenv("GET_B200_GRAPH_SPLIT");
+      use_split = e ? atoi(e) : 1;
     }
-    const bool okc = use_cluster && !p.out_p && p.out && (p.H % 4) == 0 && hq >= 2 && (hq + 1) / 2 <= 64 && (p.N % 2) == 0 && p.N <= GS_MAX_N &&
-                     aligned16(p.adj) && aligned16(p.x) && aligned16(p.out) && (!fused || aligned16(p.wp)) &&
-                     need_c <= GS_SMEM_LIMIT && p.G <= (1 << 29);
-    if (okc) {
-      void (*fn)(const GraphParams) = fused ? graph_cluster_kernel<true> : graph_cluster_kernel<false>;
-      static bool attr_c[2] = {false, false};
-      if (!attr_c[fused ? 1 : 0]) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM_LIMIT) != cudaSuccess) {
-          set_error("%s: cannot opt in to %d bytes of shared memory", name, (int)GS_SMEM_LIMIT);
+    int qs = 0;
+    size_t smem = 0;
+    const int S = (use_split && (!fused || sp_parts) && (int64_t)p.G * 8 < (int64_t)1 << 30) ? graph_split_plan(p, fused, qs, smem) : 0;
+    if (S > 0) {
+      SplitParams spp;
+      spp.g = p; spp.sp_parts = sp_parts; spp.n_sp = n_sp; spp.nsplit = S; spp.qs = qs;
+      TmapBytes fmap;
+      if (!make_tensor_map(&fmap, p.x, 1, 2, p.H, (int64_t)p.G * p.N, 1, p.H, 0, qs * 4, p.N, 1, 0)) return -3;
+      const int nqh = (qs + 15) / 16;
+      GraphSplitFn fn = graph_split_fn(fused, nqh);
+      static bool attr_s[2][5] = {};
+      if (!attr_s[fused ? 1 : 0][nqh]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_PER_CTA) != cudaSuccess) {
+          set_error("%s: cannot opt in to %d bytes of shared memory", name, (int)GP_SMEM_PER_CTA);
           (void)cudaGetLastError();
           return -2;
         }
-        attr_c[fused ? 1 : 0] = true;
+        attr_s[fused ? 1 : 0][nqh] = true;
       }
-      fn<<<2 * p.G, GC_THREADS, need_c, st>>>(p);
+      fn<<<p.G * S, GP_THREADS, smem, st>>>(spp, fmap);
       GETB_CHECK_LAUNCH(name);
       return 0;
     }
+    GETB_REQUIRE(!(fused && sp_parts), "%s: precomputed scorer projections need the column-split path (N <= %d, N %% 2 == 0, H %% 4 == 0)",
+                 name, GS_MAX_N);
   }
   {
     // single-CTA path: the whole graph (features + adjacency) staged in shared memory by TMA bulk copies
@@ -981,6 +1016,45 @@ extern "C" int get_gsl_fused_bp(const float* adj, const float* F, const float* w
   p.seed_s = seed_scorer; p.seed_2 = seed_layer2; p.salt = dropout_salt_ptr();
   p.score = score; p.keep_out = keep;
   return launch_graph(p, true, (cudaStream_t)stream, "get_gsl_fused_bp");
+}
+
+extern "C" int get_gsl_fused_sp(const float* adj, const float* F, const float* sp_parts, int n_sp, const float* gate, int G, int N,
+                                int H, int k, float drop_p, uint32_t seed_layer2, float* score, uint8_t* keep, float* out,
+                                void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream) {
+  GETB_REQUIRE(adj && F && sp_parts && n_sp >= 1 && gate && keep && (out || planes), "get_gsl_fused_sp: null pointer");
+  GETB_REQUIRE(k >= 0 && k <= N, "get_gsl_fused_sp: k=%d out of [0,%d]", k, N);
+  GETB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "get_gsl_fused_sp: dropout probability must be in [0,1)");
+  GraphParams p;
+  memset(&p, 0, sizeof(p));
+  p.adj = adj; p.x = F; p.out = out; p.G = G; p.N = N; p.H = H;
+  p.out_p = reinterpret_cast<__nv_bfloat16*>(planes); p.ld_p = ld_p; p.ps_p = plane_stride; p.np_p = nplanes;
+  p.gate = gate; p.k = k;
+  p.thr = drop_p > 0.f ? drop_threshold(drop_p) : 0;
+  p.scale = 1.0f / (1.0f - drop_p);
+  p.seed_2 = seed_layer2; p.salt = dropout_salt_ptr();
+  p.score = score; p.keep_out = keep;
+  return launch_graph(p, true, (cudaStream_t)stream, "get_gsl_fused_sp", sp_parts, n_sp);
+}
+
+extern "C" int get_graph_split_slices(int N, int H) {
+  GraphParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H;
+  p.adj = reinterpret_cast<const float*>(16); p.x = reinterpret_cast<const float*>(16);
+  int qs = 0;
+  size_t smem = 0;
+  return graph_split_plan(p, true, qs, smem);
+}
+
+extern "C" int get_rowdot_f32(const float* F, const float* w, int64_t M, int H, float drop_p, uint32_t seed, float* out,
+                              void* stream) {
+  GETB_REQUIRE(F && w && out && M >= 0 && H >= 4 && (H % 4) == 0 && aligned16(F) && aligned16(w), "get_rowdot_f32: bad arguments");
+  GETB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "get_rowdot_f32: dropout probability must be in [0,1)");
+  if (M == 0) return 0;
+  rowdot_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(F, w, M, H, drop_p > 0.f ? drop_threshold(drop_p) : 0u,
+                                                                 1.0f / (1.0f - drop_p), seed, dropout_salt_ptr(), out);
+  GETB_CHECK_LAUNCH("get_rowdot_f32");
+  return 0;
 }
 
 extern "C" int get_gsl_mask_adj_f32(const float* adj, const float* score, int G, int N, int k, float* adj_out,

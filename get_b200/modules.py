@@ -53,6 +53,7 @@ class GGNN(nn.Module):
         self.linearh1 = Linear(out_features, out_features)
         self.p_drop = float(dropout) if dropout and dropout > 0 else 0.0
         self.last_out_planes = None   # bf16 planes of the last output when requested (package-internal)
+        self.last_rowdot = None       # partial row dots of the last output when requested (package-internal)
 
     def _params(self):
         return (self.proj.linear.weight,
@@ -64,7 +65,7 @@ class GGNN(nn.Module):
                 self.linearh1.linear.weight, self.linearh1.linear.bias)
 
     def forward(self, adj, x=None, *, table=None, ids=None, keep=None, pre_agg=None, seed=None, exact_fwd=False,
-                out_planes=0):
+                out_planes=0, rowdot_of=None):
         """Reference call: forward(adj, x). Extensions used inside this package: (table, ids) = frozen embedding
         table + token ids instead of x (gather fused into the projection), keep / pre_agg from the GSL kernel,
         explicit dropout seed (tests), out_planes > 0: also keep the bf16 planes of the output (the operand of the next
@@ -73,9 +74,9 @@ class GGNN(nn.Module):
         if p > 0 and seed is None:
             seed = ops.new_seed()
         adj = adj.float()
-        out, op = ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params(), exact_fwd=exact_fwd,
-                                 out_planes=out_planes)
-        self.last_out_planes = op
+        out, op, rd = ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params(), exact_fwd=exact_fwd,
+                                     out_planes=out_planes, rowdot_of=rowdot_of)
+        self.last_out_planes, self.last_rowdot = op, rd
         return out
 
 
@@ -124,18 +125,21 @@ class GGNN_with_GSL(nn.Module):
         p = self.feat_prop2.p_drop if self.training else 0.0
         if seeds is None:
             seeds = tuple(ops.new_seed() for _ in range(3)) if self.training else (0, 0, 0)
-        f1 = self.feat_prop1(adj, feat, table=table, ids=ids, seed=seeds[0], exact_fwd=True)   # decides the kept node set
-        f1 = ops.grad_marker(f1, "feat_prop2")      # backward: feat_prop2's gradients are complete when dF1 arrives here
         wp, gate = self._scorer_params()
         ps = self.word_scorer1.p_drop if self.training else 0.0
         assert ps == p or ps == 0 or p == 0, "scorer / layer-2 dropout rates are the same value in the reference"
+        # the scorer's projection dropout_s(F1) . w_p leaves feat_prop1's last GEMM as a by-product of its epilogue
+        f1 = self.feat_prop1(adj, feat, table=table, ids=ids, seed=seeds[0], exact_fwd=True,    # decides the kept node set
+                             rowdot_of=(wp, max(p, ps), seeds[1]))
+        sp_parts = self.feat_prop1.last_rowdot
+        f1 = ops.grad_marker(f1, "feat_prop2")      # backward: feat_prop2's gradients are complete when dF1 arrives here
         # the refined aggregation leaves the fused kernel as bf16 planes: it is only ever the operand of feat_prop2's
         # projection (wrapper.py:191-192, by linearity of the bias-free proj)
         G, N, H1 = f1.shape
         tc = ops.layer_uses_tc(G * N, self.feat_prop2.out_features, H1)
         score, keep, agg = ops.gsl_fused(adj, f1.detach(), wp, gate, k, drop_p=max(p, ps), seed_scorer=seeds[1],
                                          seed_layer2=seeds[2], want_score=want_score,
-                                         planes_n=ops.gemm_mode(False) if tc else 0)
+                                         planes_n=ops.gemm_mode(False) if tc else 0, sp_parts=sp_parts)
         self.last_keep, self.last_score = keep, score
         out = self.feat_prop2(adj, f1, keep=keep, pre_agg=agg.t if tc else agg, seed=seeds[2], out_planes=out_planes)
         self.last_out_planes = self.feat_prop2.last_out_planes

@@ -440,9 +440,23 @@ def graph_aggregate(adj, x, keep=None, out=None, transpose=False, accumulate=Fal
     return out
 
 
-def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, want_score=True, planes_n: int = 0):
+def rowdot(feat2d: torch.Tensor, w: torch.Tensor, drop_p: float = 0.0, seed: int = 0) -> torch.Tensor:
+    """(M,) = dropout(feat2d) . w -- the projection of the GSL scorer GGNN(H -> 1) (wrapper.py:158,167,191)."""
+    _chk_f32(feat2d, "feat"); _chk_f32(w, "w")
+    M, H = feat2d.shape
+    out = torch.empty((1, M), dtype=torch.float32, device=feat2d.device)
+    _lib.check(_lib.load().get_rowdot_f32(feat2d.data_ptr(), w.data_ptr(), M, H, float(drop_p), seed & 0xFFFFFFFF, out.data_ptr(),
+                                          _stream()), "get_rowdot_f32")
+    return out
+
+
+def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, want_score=True, planes_n: int = 0,
+              sp_parts: Optional[torch.Tensor] = None):
     """Fused scorer -> top-k -> refined aggregation. Returns (score (G,N) | None, keep (G,N) uint8, out): out is fp32
-    (G,N,H), or with planes_n > 0 the refined aggregation as bf16 Planes (G*N, H) for the layer-2 projection."""
+    (G,N,H), or with planes_n > 0 the refined aggregation as bf16 Planes (G*N, H) for the layer-2 projection.
+    sp_parts (n, G*N): the scorer projection dropout_s(feat) . wp precomputed as partial sums (by-product of the GEMM that
+    wrote feat); computed here by a row-dot kernel when absent. Shapes the column-split kernel does not cover (N > 128)
+    take the one-CTA-per-graph kernel."""
     lib = _lib.load()
     _chk_f32(adj, "adj"); _chk_f32(feat, "feat"); _chk_f32(wp, "wp"); _chk_f32(gate, "gate")
     G, N, H = feat.shape
@@ -451,26 +465,38 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     score = torch.empty((G, N), dtype=torch.float32, device=feat.device) if want_score else None
     keep = torch.empty((G, N), dtype=torch.uint8, device=feat.device)
     out = alloc_planes(planes_n, G * N, H, feat.device) if planes_n else torch.empty_like(feat)
+    split = int(lib.get_graph_split_slices(N, H)) > 0 and os.environ.get("GET_B200_GRAPH_SPLIT", "1") != "0"
+    if split and sp_parts is None:
+        sp_parts = rowdot(feat.view(G * N, H), wp, drop_p, seed_scorer)
+    if not split:
+        sp_parts = None
+    rec = (adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF, score, keep, out, sp_parts)
     if PROFILE_GSL_ARGS is not None:
-        PROFILE_GSL_ARGS.append((adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF,
-                                 seed_layer2 & 0xFFFFFFFF, score, keep, out))
+        PROFILE_GSL_ARGS.append(rec)
     prof = PROFILE_GSL_EVENTS
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _gsl_launch(adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF, score, keep, out)
+    _gsl_launch(*rec)
     if prof is not None:
         e1.record()
         prof.append((e0, e1, G))
     return score, keep, out
 
 
-def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out):
+def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out, sp_parts=None):
     lib = _lib.load()
     G, N, H = feat.shape
-    if isinstance(out, Planes):
+    pl = out if isinstance(out, Planes) else None
+    if sp_parts is not None:
+        assert sp_parts.is_contiguous() and sp_parts.shape[1] == G * N
+        _lib.check(lib.get_gsl_fused_sp(adj.data_ptr(), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0], gate.data_ptr(), G, N,
+                                        H, k, drop_p, s2, _ptr(score), keep.data_ptr(), None if pl else out.data_ptr(),
+                                        pl.ptr if pl else None, pl.ld if pl else 0, pl.plane_stride if pl else 0,
+                                        pl.nplanes if pl else 0, _stream()), "get_gsl_fused_sp")
+    elif pl is not None:
         _lib.check(lib.get_gsl_fused_bp(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k, drop_p, s1, s2,
-                                        _ptr(score), keep.data_ptr(), None, out.ptr, out.ld, out.plane_stride, out.nplanes,
+                                        _ptr(score), keep.data_ptr(), None, pl.ptr, pl.ld, pl.plane_stride, pl.nplanes,
                                         _stream()), "get_gsl_fused_bp")
     else:
         _lib.check(lib.get_gsl_fused_f32(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k, drop_p, s1,
@@ -479,9 +505,8 @@ def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out):
 
 def gsl_fused_replay(rec):
     """Re-issue one recorded fused GSL launch (PROFILE_GSL_ARGS entry) with the same inputs and output buffers."""
-    adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out = rec
-    _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out)
-    return feat.shape[0]
+    _gsl_launch(*rec)
+    return rec[1].shape[0]
 
 
 def gsl_mask_adj(adj, score, k):
@@ -573,7 +598,8 @@ class GGNNLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, adj, feat, table, ids, keep, pre_agg, p_drop, seed,
-                Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, exact_fwd=False, out_planes=0):
+                Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, exact_fwd=False, out_planes=0,
+                rd_w=None, rd_p=0.0, rd_seed=0):
         G, N = adj.shape[0], adj.shape[1]
         M = G * N
         H, Din = Wp.shape
@@ -609,16 +635,24 @@ class GGNNLayerFn(torch.autograd.Function):
                 epilogue=BPE_ZR, C=z, out1=r, bias=pzr.bias, aux0=x, planes_out=rxP, zr=(gs, H), tn=bn)
         ph = pk["h"]()
         op = alloc_planes(out_planes, M, H, dev) if out_planes else None
+        # row-dot by-product: the scorer projection dropout_s(out) . w_p in partial sums per N tile half (the fused GSL kernel
+        # adds them up), so that kernel never needs whole feature rows
+        rd = None
+        if rd_w is not None:
+            n_cols = round_up(H, 8) if op is not None else H       # columns the launch tiles (planes add the padding)
+            rd = torch.empty((2 * ((n_cols + bn - 1) // bn), M), dtype=torch.float32, device=dev)
         gemm_bp([(aP, ph.planes.view_cols(0, H), H), (rxP, ph.planes.view_cols(Hp, H), H)], M, H, mode=mode,
-                epilogue=BPE_TANH_BLEND, C=out, out1=h, bias=ph.bias, aux0=z, aux1=x, planes_out=op)
+                epilogue=BPE_TANH_BLEND, C=out, out1=h, bias=ph.bias, aux0=z, aux1=x, planes_out=op, tn=bn,
+                rowdot=(rd_w, rd, rd_p, rd_seed) if rd is not None else None)
         ctx.save_for_backward(adj, keep, xd.t, xar.t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1)
         ctx.p_drop, ctx.seed, ctx.dims, ctx.has_feat, ctx.gs = p_drop, seed, (G, N, H, Din), feat is not None, gs
         op_t = op.t if op is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)
-        ctx.mark_non_differentiable(op_t)
-        return out.view(G, N, H), op_t
+        rd_t = rd if rd is not None else torch.empty(0, dtype=torch.float32, device=dev)
+        ctx.mark_non_differentiable(op_t, rd_t)
+        return out.view(G, N, H), op_t, rd_t
 
     @staticmethod
-    def backward(ctx, dout, _dplanes):
+    def backward(ctx, dout, _dplanes, _drd):
         (adj, keep, xd_t, xar_t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1) = ctx.saved_tensors
         G, N, H, Din = ctx.dims
         M = G * N
@@ -649,7 +683,7 @@ class GGNNLayerFn(torch.autograd.Function):
         dxP = alloc_planes(mode, M, H, dev)
         graph_aggregate(adj, da.view(G, N, H), keep, out=dx.view(G, N, H), transpose=True, accumulate=True, planes_out=dxP)
         need = ctx.needs_input_grad
-        grads = [None] * 23
+        grads = [None] * 26
         # order of inputs: ... 8:Wp 9:Wz0 10:bz0 11:Wz1 12:bz1 13:Wr0 14:br0 15:Wr1 16:br1 17:Wh0 18:bh0 19:Wh1 20:bh1
         xP, aP1, rxP = xar.view_cols(0, H), xar.view_cols(Hp, Hp), xar.view_cols(2 * Hp, H)
         if need[9] or need[13] or need[17] or need[10] or need[14] or need[18]:
@@ -796,18 +830,21 @@ def layer_uses_tc(M: int, H: int, Din: int) -> bool:
 
 
 def ggnn_layer(adj, feat, table, ids, keep, pre_agg, p_drop, seed, params: Sequence[torch.Tensor], exact_fwd: bool = False,
-               out_planes: int = 0):
+               out_planes: int = 0, rowdot_of=None):
     """exact_fwd=True: the forward contractions stay fp32-exact in every precision mode (feat_prop1: GSL top-k chain).
-    Returns (out, planes tensor of out | None). Large regular shapes run on the tensor cores; the rest on the SIMT path."""
+    rowdot_of = (w (H,), p, seed): also return the partial row dots dropout(out; p, seed) . w (the GSL scorer projection).
+    Returns (out, planes tensor of out | None, row-dot partial sums | None). Large regular shapes run on the tensor cores;
+    the rest on the SIMT path."""
     H, Din = params[0].shape
     M = adj.shape[0] * adj.shape[1]
     if layer_uses_tc(M, H, Din):
-        out, op = GGNNLayerFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params, bool(exact_fwd),
-                                    int(out_planes))
-        return out, (op if out_planes else None)
+        rd_w, rd_p, rd_seed = rowdot_of if rowdot_of is not None else (None, 0.0, 0)
+        out, op, rd = GGNNLayerFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params, bool(exact_fwd),
+                                        int(out_planes), rd_w, float(rd_p), int(rd_seed))
+        return out, (op if out_planes else None), (rd if rowdot_of is not None else None)
     if isinstance(pre_agg, torch.Tensor) and pre_agg.dtype == torch.bfloat16:
         pre_agg = Planes(pre_agg, Din).to_float().view(adj.shape[0], adj.shape[1], Din)
-    return GGNNLayerSimtFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params, bool(exact_fwd)), None
+    return GGNNLayerSimtFn.apply(adj, feat, table, ids, keep, pre_agg, float(p_drop), int(seed), *params, bool(exact_fwd)), None, None
 
 
 # =================================================================================================

@@ -257,7 +257,7 @@ def gemm_bp(segments: Sequence[Tuple[Planes, Planes, int]], M: int, N: int, *, m
             aux0: Optional[torch.Tensor] = None, aux1: Optional[torch.Tensor] = None, planes_out: Optional[Planes] = None,
             planes_out_n: int = 0, pad_one: bool = False, accumulate: bool = False, group_rows: int = 0,
             zr: Optional[Tuple[int, int]] = None, drop_out: Optional[Tuple[float, int]] = None, tn: int = 0,
-            split_k: int = 1, workspace: Optional[torch.Tensor] = None, kblock: int = 0):
+            split_k: int = 1, workspace: Optional[torch.Tensor] = None, kblock: int = 0, rowdot=None):
     """acc[m,n] = sum_s A_s(m,:) . B_s(n,:) on the tensor cores; see include/get_b200.h (get_gemm_bp) for the epilogues."""
     lib = _lib.load()
     d = _lib.GemmBpDesc()
@@ -289,6 +289,13 @@ def gemm_bp(segments: Sequence[Tuple[Planes, Planes, int]], M: int, N: int, *, m
     if drop_out is not None and drop_out[0] > 0:
         d.drop_out_p, d.drop_out_seed = float(drop_out[0]), int(drop_out[1]) & 0xFFFFFFFF
     d.split_k, d.kblock = int(split_k), int(kblock)
+    if rowdot is not None:           # (w (N,), out (parts, M), p, seed): TANH_BLEND row-dot by-product
+        rw, ro, rp, rs = rowdot
+        d.rowdot_w, d.rowdot_out, d.rowdot_p, d.rowdot_seed = rw.data_ptr(), ro.data_ptr(), float(rp), int(rs) & 0xFFFFFFFF
+        d.rowdot_out = None
+        parts = int(lib.get_gemm_bp_rowdot_parts(ct.byref(d)))
+        assert parts == ro.shape[0] and ro.shape[1] == M and ro.is_contiguous() and rw.is_contiguous(), (parts, tuple(ro.shape))
+        d.rowdot_out = ro.data_ptr()
     if workspace is not None:
         d.workspace, d.workspace_floats = workspace.data_ptr(), workspace.numel()
     _lib.check(lib.get_gemm_bp(ct.byref(d), _stream()), "get_gemm_bp")

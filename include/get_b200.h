@@ -165,6 +165,12 @@ typedef struct get_gemm_bp_desc {
   int32_t split_k;
   int32_t kblock;           /* k elements per pipeline stage: 32 or 64; 0 = library choice */
   float* workspace; int64_t workspace_floats;
+  /* TANH_BLEND only: row-dot by-product of the blended output (the `proj` of the GSL scorer GGNN(H -> 1),
+   * wrapper.py:158,167,191, with the scorer's own nn.Dropout draw): partial sums per N tile and tile half,
+   * rowdot_out[(n_tile*2 + half)*M + m] = sum_n dropout(out[m,n]; rowdot_p, rowdot_seed, index m*N + n) * rowdot_w[n];
+   * get_gemm_bp_rowdot_parts(desc) partial vectors in total, summed (fixed order) by the fused GSL kernel. */
+  const float* rowdot_w; float* rowdot_out;
+  float rowdot_p; uint32_t rowdot_seed;
 } get_gemm_bp_desc;
 
 /* 0 = launched; negative = invalid / unsupported descriptor (the Python host then raises: there is no silent fallback) */
@@ -174,6 +180,7 @@ int get_gemm_bp(const get_gemm_bp_desc* desc, void* stream);
 int get_gemm_bp_tile_n(int M, int N, int mode);
 int64_t get_gemm_bp_ws_ld(const get_gemm_bp_desc* desc);
 int get_gemm_bp_splits(const get_gemm_bp_desc* desc);
+int get_gemm_bp_rowdot_parts(const get_gemm_bp_desc* desc);   /* 2 * number of N tiles */
 
 /* Fixed-order reduction of split-K partial tiles into up to GET_BP_MAX_DST destination blocks (the weight / bias
  * gradients, written straight into the flat gradient bucket): for every block b and (r, c) inside it
@@ -242,6 +249,20 @@ int get_graph_aggregate_bp(const float* adj, const float* x, const uint8_t* keep
 int get_gsl_fused_bp(const float* adj, const float* F, const float* wp, const float* gate, int G, int N, int H, int k,
                      float drop_p, uint32_t seed_scorer, uint32_t seed_layer2, float* score, uint8_t* keep,
                      float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
+
+/* The fused GSL kernel with the scorer projection s_p = dropout_s(F) . w_p PRECOMPUTED (n_sp partial vectors of G*N floats,
+ * summed in order): a by-product of the epilogue of the contraction that wrote F (get_gemm_bp, rowdot_out), or of
+ * get_rowdot_f32. Without the need for whole feature rows every graph is processed by several independent CTAs that own
+ * column slices of F (two co-resident per SM: loads and stores of one overlap the compute of the other). Same outputs as
+ * get_gsl_fused_bp; drop_p / seed_layer2 = the nn.Dropout draw of feat_prop2 (the scorer's draw went into s_p). */
+int get_gsl_fused_sp(const float* adj, const float* F, const float* sp_parts, int n_sp, const float* gate, int G, int N,
+                     int H, int k, float drop_p, uint32_t seed_layer2, float* score, uint8_t* keep, float* out,
+                     void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
+/* Column slices per graph the split kernels use for (N, H); 0 = shape not covered (N > 128, odd N, H % 4 != 0, ...): then
+ * get_gsl_fused_f32 / _bp (one CTA per graph, or the generic kernel) are the entry points. */
+int get_graph_split_slices(int N, int H);
+/* out[m] = dropout(F[m,:]; drop_p, seed, index m*H + c) . w   (the `proj` of GGNN(H -> 1), wrapper.py:191). */
+int get_rowdot_f32(const float* F, const float* w, int64_t M, int H, float drop_p, uint32_t seed, float* out, void* stream);
 
 /* GSL.forward as a stand-alone op (wrapper.py:215-227): adj_out = adj * mask(top-k(score)). score (G,N). */
 int get_gsl_mask_adj_f32(const float* adj, const float* score, int G, int N, int k,
