@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid
   const uint32_t salt = (FUSED && p.thr) ? __ldg(p.salt) : 0u;
   const uint32_t seed_2 = p.seed_2 + salt;
 
-  float* sF = smem;
+  float* sF = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~(uintptr_t)127);   // TMA destination: 128-byte aligned
   float* sA = sF + (size_t)N * WP;
   float* s_sp = sA + (size_t)N * N;
   float* s_score = s_sp + N;
@@ -575,6 +575,13 @@ __global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid
   uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_rank + N);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_keep + ((N + 15) & ~15));   // [0] adjacency, [1] features
 
+#ifdef GETB_GRAPH_TIMELINE
+  __shared__ long long tl[10];
+  const long long t0 = clock64();
+#define GP_T(i) do { if (tid == 0) tl[i] = clock64() - t0; } while (0)
+#else
+#define GP_T(i) do { } while (0)
+#endif
   const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
   if (tid == 0) {
     gs_mbar_init(&bars[0], 1);
@@ -600,7 +607,9 @@ __global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid
   }
 
   // ---- neighbour lists in place: row i -> {byte offset of F row j, w_ij}; rows with more than N/2 neighbours stay dense
+  GP_T(0);
   gs_mbar_wait(&bars[0], 0);
+  GP_T(1);
   {
     float wv[GP_ROWS_PER_WARP][4];
 #pragma unroll
@@ -646,6 +655,7 @@ __global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid
     }
   }
   __syncthreads();
+  GP_T(2);
 
   const float inv_rowbytes = 1.0f / (float)(WP * 4);   // offsets are exact multiples of WP*4 < 2^24: rounding recovers j
   if (FUSED) {
@@ -699,7 +709,9 @@ __global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid
   }
 
   // ---- features have landed: the layer-2 dropout draw is applied in place -----------------------------------------
+  GP_T(3);
   gs_mbar_wait(&bars[1], 0);
+  GP_T(4);
   if (FUSED && p.thr) {
     for (int e = tid; e < N * WQ; e += GP_THREADS) {
       const int i = e / WQ, q = e - i * WQ;
@@ -710,6 +722,7 @@ __global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid
     }
   }
   __syncthreads();
+  GP_T(5);
 
   // ---- out[i, own columns] = sum_e w[i][e] * x[idx[i][e], own columns]; half a warp per row ------------------------
   const bool masked = FUSED || (p.keep_in != nullptr);
@@ -779,6 +792,13 @@ __global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid
       planes_store4(p.out_p + ((int64_t)g * N + i) * p.ld_p + H + hl * 4, p.ps_p, p.np_p, vv);
     }
   }
+#ifdef GETB_GRAPH_TIMELINE
+  __syncthreads();
+  GP_T(6);
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 150 || blockIdx.x == 400))
+    printf("GPDBG cta %d: init %lld adj_landed %lld lists %lld scores %lld F_landed %lld dropout %lld aggregate+store %lld\n", blockIdx.x,
+           tl[0], tl[1], tl[2], tl[3], tl[4], tl[5], tl[6]);
+#endif
 }
 
 // s_p[m] = dropout_s(F[m,:]) . wp  -- the scorer projection for the stand-alone entry points (in the model it is a by-product
@@ -882,7 +902,7 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
     static int use_split = -1;
     if (use_split < 0) {
       const char* e = getenv("GET_B200_GRAPH_SPLIT");
-      use_split = e ? atoi(e) : 1;
+      use_split = e ? atoi(e) : 0;   // measured slower than one CTA per graph on B200 (issue-bound phases are duplicated per slice)
     }
     int qs = 0;
     size_t smem = 0;
@@ -896,10 +916,17 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
       GraphSplitFn fn = graph_split_fn(fused, nqh);
       static bool attr_s[2][5] = {};
       if (!attr_s[fused ? 1 : 0][nqh]) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_PER_CTA) != cudaSuccess) {
+        // two CTAs per SM need the full shared-memory carve-out (the default carve-out only guarantees ONE resident CTA)
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_PER_CTA) != cudaSuccess ||
+            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
           set_error("%s: cannot opt in to %d bytes of shared memory", name, (int)GP_SMEM_PER_CTA);
           (void)cudaGetLastError();
           return -2;
+        }
+        if (getenv("GET_B200_GRAPH_DEBUG")) {
+          int nb = 0;
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, GP_THREADS, smem);
+          fprintf(stderr, "graph_split_kernel<%d,%d>: %d slices, %zu B smem, %d CTAs/SM\n", (int)fused, nqh, S, smem, nb);
         }
         attr_s[fused ? 1 : 0][nqh] = true;
       }

@@ -465,7 +465,7 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     score = torch.empty((G, N), dtype=torch.float32, device=feat.device) if want_score else None
     keep = torch.empty((G, N), dtype=torch.uint8, device=feat.device)
     out = alloc_planes(planes_n, G * N, H, feat.device) if planes_n else torch.empty_like(feat)
-    split = int(lib.get_graph_split_slices(N, H)) > 0 and os.environ.get("GET_B200_GRAPH_SPLIT", "1") != "0"
+    split = int(lib.get_graph_split_slices(N, H)) > 0 and os.environ.get("GET_B200_GRAPH_SPLIT", "0") != "0"
     if split and sp_parts is None:
         sp_parts = rowdot(feat.view(G * N, H), wp, drop_p, seed_scorer)
     if not split:
