@@ -162,9 +162,19 @@ def make_batches(w, n, base_seed, n_claims=None):
 
 
 def graph_kernel_bytes(w, pairs):
-    """ALGORITHMIC bytes of the fused GSL kernel per launch: read F1 + adjacency, write the refined
-    aggregation (two bf16 planes = 4 bytes per element, like the fp32 the formula was written for): 4*R*(2H+R) per pair."""
+    """SURVEY.md 8(d)'s per-pair figure for the GSL path: read F1 + the dense adjacency, write the refined aggregation
+    (two bf16 planes = 4 bytes per element, like the fp32 the formula was written for): 4*R*(2H+R) per pair. Since round 2
+    the adjacency is read by the list builder (once per step, for five consumers), not by the fused kernel."""
     return pairs * 4 * w.len_right * (2 * w.hidden + w.len_right)
+
+
+def gsl_kernel_own_bytes(w, pairs, nnz_per_pair, n_sp, planes):
+    """Bytes the fused GSL kernel itself has to move per launch: F1 read once (4RH), refined aggregation written once
+    (`planes` bf16 planes, or fp32 when planes = 0), neighbour lists (8 B per edge + 4 B per row), scorer projection partial
+    sums (4 B x n_sp per row), score + keep written (5 B per row)."""
+    R, H = w.len_right, w.hidden
+    out = 2 * planes * R * (((H + 7) // 8) * 8) if planes else 4 * R * H
+    return pairs * (4 * R * H + out + 8 * nnz_per_pair + 4 * R + 4 * n_sp * R + 5 * R)
 
 
 def config_dict(w):
@@ -339,6 +349,34 @@ def torch_cuda_baseline(w, dev, model_ours, iters=10):
                     "same 4 batches; fwd_bwd = zero_grad + forward + CE + backward + Adam in train mode"}
 
 
+def graph_timed_ms(fn, reps=3):
+    """Device time of fn() (a sequence of launches on the current stream) with the host out of the picture: the launches
+    are captured ONCE into a CUDA graph and the graph replay is timed between two events (median of `reps` replays after
+    one warm-up replay). A Python / ctypes launch costs ~10 us of host time -- more than some of the kernels measured."""
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()                                    # warm-up outside capture (lazy module loads, attribute opt-ins)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+        g.replay()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+    torch.cuda.current_stream().wait_stream(side)
+    del g
+    return float(np.median(ms))
+
+
 def stream_roofline(w, dev, graphs=7680, iters=10, sweep=False):
     """The fused GSL kernel at streaming size (BASELINE.json configs[4]: thousands of claim-evidence graphs resident, Snopes
     dims; SURVEY.md 8(d) asks for the roofline at B1 >= 1e4-ish sizes too). Inputs (2 sets, alternated) exceed L2.
@@ -363,34 +401,46 @@ def stream_roofline(w, dev, graphs=7680, iters=10, sweep=False):
     feats = [torch.randn(graphs, N, H, device=dev) for _ in range(2)]
 
     def run(adj, k, p):
-        # the scorer projection arrives precomputed, as in the model (by-product of the GEMM that writes the features)
+        # the scorer projection arrives precomputed, as in the model (by-product of the GEMM that writes the features), and
+        # so do the neighbour lists (built once per step, shared by five consumers)
         sps = [ops.rowdot(f.view(graphs * N, H), wp, p, 1) for f in feats]
-        for i in range(3):
-            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl, sp_parts=sps[i % 2])
-        evs = []
-        for i in range(iters):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            ops.gsl_fused(adj, feats[i % 2], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl, sp_parts=sps[i % 2])
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        lists = ops.NeighborLists(adj)
+        recs = []
+        ops.PROFILE_GSL_ARGS = recs
+        for i in range(2):
+            ops.gsl_fused(lists, feats[i], wp, gate, k, drop_p=p, seed_scorer=1, seed_layer2=2, planes_n=npl, sp_parts=sps[i])
+        ops.PROFILE_GSL_ARGS = None
+        return graph_timed_ms(lambda: [ops.gsl_fused_replay(recs[i % 2]) for i in range(iters)]) / iters
 
-    nbytes = graphs * 4 * N * (2 * H + N)
-    out = {"graphs": graphs, "algorithmic_bytes_per_launch": nbytes, "peak": peak, "unit": "GB/s"}
+    class _W(object):
+        len_right, hidden = N, H
+
+    def own_bytes(nnz):
+        return float(gsl_kernel_own_bytes(_W, graphs, nnz, 1, npl))
+
+    out = {"graphs": graphs, "peak": peak, "unit": "GB/s",
+           "bytes": "kernel-own bytes (F1 read + aggregation written + lists + scorer partial sums), see roofline.bytes",
+           "timing": "10 launches captured in one CUDA graph, alternating two input sets (2 x 0.9 GB > L2)"}
     adj, nnz = adj_set(w.window)
+    nbytes = own_bytes(nnz)
+    out["algorithmic_bytes_per_launch"] = nbytes
     for name, p in (("eval", 0.0), ("train_p0.2", 0.2)):
         ms = run(adj, int(w.gsl_rate * N), p)
         out[name] = {"avg_launch_ms": ms, "achieved": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+    lists = ops.NeighborLists(adj)
+    bms = graph_timed_ms(lambda: [lists.rebuild() for _ in range(4)]) / 4
+    dense_bytes = graphs * (4 * N * N + 2 * (8 * nnz + 4 * N))
+    out["list_build"] = {"avg_launch_ms": bms, "bytes": dense_bytes, "achieved": dense_bytes / bms / 1e6, "frac": dense_bytes / bms / 1e6 / peak}
+    del lists
     if sweep:
         rows = []
         for window in (3, 5, 9):
             adj, nnz = adj_set(window)
+            nb = own_bytes(nnz)
             for rate in (0.3, 0.6, 0.9):
                 ms = run(adj, int(rate * N), 0.2)
                 rows.append({"gnn_window_size": window, "gsl_rate": rate, "nnz_per_graph": nnz, "avg_launch_ms": ms,
-                             "achieved": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak})
+                             "algorithmic_bytes_per_launch": nb, "achieved": nb / ms / 1e6, "frac": nb / ms / 1e6 / peak})
         out["sweep_train"] = rows
     return out
 
@@ -678,18 +728,18 @@ def run_ours(args):
             loss.backward()
         torch.cuda.synchronize()
         recs, ops.PROFILE_GSL_ARGS = ops.PROFILE_GSL_ARGS, None
-        # (2) exactly those launches (same adjacency / layer-1 features / dropout seeds, ~60 MB of distinct inputs each,
-        #     ~1 GB in total > L2) replayed back to back between two events: the GPU never waits for the host, so the
-        #     event interval is kernel time. Three passes, the first is a warm-up.
-        for rep in range(3):
-            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e_a.record()
-            ngraphs = [ops.gsl_fused_replay(r) for r in recs]
-            e_b.record()
-            torch.cuda.synchronize()
-            if rep > 0:
-                gsl_ms.append(e_a.elapsed_time(e_b) / len(recs))
-                gsl_pairs.append(float(np.mean(ngraphs)))
+        # (2) exactly those launches (same neighbour lists / layer-1 features / dropout seeds, ~55 MB of distinct inputs and
+        #     outputs each, ~1 GB in total > L2) captured into one CUDA graph and replayed between two events: the GPU never
+        #     waits for the host, so the event interval is kernel time.
+        ngraphs = [r[1].shape[0] for r in recs]
+        for rep in range(2):
+            gsl_ms.append(graph_timed_ms(lambda: [ops.gsl_fused_replay(r) for r in recs]) / len(recs))
+            gsl_pairs.append(float(np.mean(ngraphs)))
+        gsl_mode = recs[0][12]
+        gsl_nnz = float(np.mean([float(r[0].cnt.sum().item()) / r[1].shape[0] for r in recs])) if gsl_mode == "lists" else None
+        gsl_nsp = int(recs[0][11].shape[0]) if recs[0][11] is not None else 0
+        gsl_planes = recs[0][10].nplanes if hasattr(recs[0][10], "nplanes") else 0
+        build_ms = (graph_timed_ms(lambda: [r[0].rebuild() for r in recs]) / len(recs)) if gsl_mode == "lists" else 0.0
         real_pairs = float(np.mean([batches[(i + args.warmup) % NBATCH]["pairs"] for i in range(min(args.steps, NBATCH))]))
         del recs
         if world == 1 and not args.quick:
@@ -718,7 +768,11 @@ def run_ours(args):
         gsl_avg_ms = float(np.mean(gsl_ms)) if gsl_ms else None
         # algorithmic bytes on the REAL pairs of the batches (the launches also carry the dummy pairs that pad the batch to a
         # multiple of 16: they are work of the launch but not of the workload)
-        gsl_bytes = float(graph_kernel_bytes(w, real_pairs)) if gsl_ms else None
+        survey_bytes = float(graph_kernel_bytes(w, real_pairs)) if gsl_ms else None
+        if gsl_ms and gsl_mode == "lists":
+            gsl_bytes = float(gsl_kernel_own_bytes(w, real_pairs, gsl_nnz, gsl_nsp, gsl_planes))
+        else:
+            gsl_bytes = survey_bytes
         achieved = gsl_bytes / (gsl_avg_ms * 1e-3) / 1e9 if gsl_ms else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gsl_fused_traffic.json")
@@ -760,11 +814,17 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "passes_ms_per_step": [1e3 * t / args.steps for t in e2e_times], "reported": "median of 3 passes of K steps"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "fused GSL graph kernel (get_gsl_fused_bp), train-mode dropout, the bench batches' own launches replayed back to back",
+            "roofline": {"kernel": "fused GSL graph kernel (get_gsl_gather: scorer + top-k + refined aggregation on neighbour lists), train-mode "
+                                   "dropout, the bench batches' own launches replayed from one CUDA graph",
                          "bound": "hbm", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "avg_launch_ms": gsl_avg_ms, "algorithmic_bytes_per_launch": gsl_bytes,
+                         "bytes": "F1 read + refined aggregation written + neighbour lists + scorer partial sums (the dense adjacency is read "
+                                  "by the list builder, once per step for five consumers)",
+                         "list_build_ms": build_ms if gsl_ms else None,
+                         "survey_formula": ({"bytes_per_launch": survey_bytes, "note": "4R(2H+R) per pair incl. the dense adjacency, over fused kernel + list build time",
+                                             "frac": survey_bytes / ((gsl_avg_ms + build_ms) * 1e-3) / 1e9 / peak} if gsl_ms else None),
                          "bytes_counted_on": "real pairs (%.1f per launch; launches carry %.1f incl. padding)" % (real_pairs, float(np.mean(gsl_pairs)) if gsl_pairs else 0.0),
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
             "e2e_token_inputs": e2e_tok,

@@ -73,7 +73,7 @@ class GGNN(nn.Module):
         p = self.p_drop if self.training else 0.0
         if p > 0 and seed is None:
             seed = ops.new_seed()
-        adj = adj.float()
+        adj = ops.as_lists(adj if isinstance(adj, ops.NeighborLists) else adj.float())
         out, op, rd = ops.ggnn_layer(adj, x, table, ids, keep, pre_agg, p, seed or 0, self._params(), exact_fwd=exact_fwd,
                                      out_planes=out_planes, rowdot_of=rowdot_of)
         self.last_out_planes, self.last_rowdot = op, rd
@@ -119,8 +119,9 @@ class GGNN_with_GSL(nn.Module):
         return wp, gate
 
     def forward(self, adj, feat=None, *, table=None, ids=None, seeds=None, want_score=True, out_planes=0):
-        adj = adj.float().contiguous()
-        n = adj.shape[-1]
+        # ONE pass over the dense adjacency: neighbour lists shared by both layers, the GSL kernel and the backward pass
+        adj = ops.as_lists(adj if isinstance(adj, ops.NeighborLists) else adj.float())
+        n = adj.N
         k = int(self.gsl1.rate * n)
         p = self.feat_prop2.p_drop if self.training else 0.0
         if seeds is None:

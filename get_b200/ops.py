@@ -417,23 +417,79 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
     return out
 
 
+GL_MAX_N = 232          # graph_lists.cu
+
+
+class NeighborLists(object):
+    """Packed neighbour lists of a batch of dense adjacencies (G,N,N), built ONCE per step by one kernel and walked by every
+    aggregation of the step (layer-1 and GSL-refined aggregation, the scorer's adj @ s_p, both adj^T products of the
+    backward pass) instead of re-scanning the 4-13 % dense matrix. `adj` stays available for
+    the dense fallback kernels (N > 256, feature widths that are not multiples of 4)."""
+
+    def __init__(self, adj: torch.Tensor):
+        _chk_f32(adj, "adj")
+        assert adj.dim() == 3 and adj.shape[1] == adj.shape[2]
+        self.adj = adj.contiguous()
+        self.G, self.N = int(adj.shape[0]), int(adj.shape[1])
+        self.shape, self.device = self.adj.shape, adj.device
+        self.nbr = self.cnt = self.nbr_t = self.cnt_t = None
+        if self.N <= GL_MAX_N and os.environ.get("GET_B200_GRAPH_LISTS", "1") != "0":
+            G, N = self.G, self.N
+            self.nbr = torch.empty((G, N, N, 2), dtype=torch.float32, device=adj.device)
+            self.nbr_t = torch.empty((G, N, N, 2), dtype=torch.float32, device=adj.device)
+            self.cnt = torch.empty((G, N), dtype=torch.int32, device=adj.device)
+            self.cnt_t = torch.empty((G, N), dtype=torch.int32, device=adj.device)
+            self.rebuild()
+
+    def rebuild(self):
+        """Re-pack after the dense adjacency changed in place."""
+        if self.nbr is not None:
+            _lib.check(_lib.load().get_build_neighbor_lists(self.adj.data_ptr(), self.G, self.N, self.nbr.data_ptr(), self.cnt.data_ptr(),
+                                                            self.nbr_t.data_ptr(), self.cnt_t.data_ptr(), _stream()),
+                       "get_build_neighbor_lists")
+        return self
+
+    def usable(self, H: int) -> bool:
+        return self.nbr is not None and H % 4 == 0 and 4 <= H <= 1024
+
+
+def as_lists(adj) -> NeighborLists:
+    return adj if isinstance(adj, NeighborLists) else NeighborLists(adj)
+
+
+def dense_adj(adj) -> torch.Tensor:
+    return adj.adj if isinstance(adj, NeighborLists) else adj
+
+
 def graph_aggregate(adj, x, keep=None, out=None, transpose=False, accumulate=False, planes_out: Optional[Planes] = None,
                     pad_one: bool = False, want_f32: bool = True):
-    """out[g] (+)= op(adj'[g]) @ x[g]; optionally also (or only, want_f32=False) as bf16 planes for the next contraction."""
+    """out[g] (+)= op(adj'[g]) @ x[g]; optionally also (or only, want_f32=False) as bf16 planes for the next contraction.
+    adj: dense (G,N,N) tensor, or NeighborLists (then the list kernel runs)."""
     lib = _lib.load()
-    _chk_f32(adj, "adj"); _chk_f32(x, "x")
+    _chk_f32(x, "x")
     G, N, H = x.shape
-    assert adj.shape == (G, N, N) and adj.is_contiguous() and x.is_contiguous()
+    assert tuple(adj.shape) == (G, N, N) and x.is_contiguous()
     if out is None and want_f32:
         assert not accumulate
         out = torch.empty_like(x)
     if keep is not None:
         assert keep.dtype == torch.uint8 and keep.shape == (G, N) and keep.is_contiguous()
+    if planes_out is not None:
+        assert planes_out.rows == G * N and planes_out.cols == H
+    if isinstance(adj, NeighborLists) and adj.usable(H):
+        nbr, cnt = (adj.nbr_t, adj.cnt_t) if transpose else (adj.nbr, adj.cnt)
+        pl = planes_out
+        _lib.check(lib.get_graph_gather(nbr.data_ptr(), cnt.data_ptr(), x.data_ptr(), _ptr(keep), _ptr(out), pl.ptr if pl else None,
+                                        pl.ld if pl else 0, pl.plane_stride if pl else 0, pl.nplanes if pl else 0, int(pad_one),
+                                        G, N, H, int(accumulate), _stream()), "get_graph_gather")
+        return out
+    adj = dense_adj(adj)
+    _chk_f32(adj, "adj")
+    assert adj.is_contiguous()
     if planes_out is None:
         _lib.check(lib.get_graph_aggregate_f32(adj.data_ptr(), x.data_ptr(), _ptr(keep), out.data_ptr(), G, N, H,
                                                int(transpose), int(accumulate), _stream()), "get_graph_aggregate_f32")
     else:
-        assert planes_out.rows == G * N and planes_out.cols == H
         _lib.check(lib.get_graph_aggregate_bp(adj.data_ptr(), x.data_ptr(), _ptr(keep), _ptr(out), planes_out.ptr, planes_out.ld,
                                               planes_out.plane_stride, planes_out.nplanes, int(pad_one), G, N, H,
                                               int(transpose), int(accumulate), _stream()), "get_graph_aggregate_bp")
@@ -454,23 +510,28 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
               sp_parts: Optional[torch.Tensor] = None):
     """Fused scorer -> top-k -> refined aggregation. Returns (score (G,N) | None, keep (G,N) uint8, out): out is fp32
     (G,N,H), or with planes_n > 0 the refined aggregation as bf16 Planes (G*N, H) for the layer-2 projection.
+    adj: NeighborLists (the list kernel: default) or a dense tensor (lists are built here).
     sp_parts (n, G*N): the scorer projection dropout_s(feat) . wp precomputed as partial sums (by-product of the GEMM that
-    wrote feat); computed here by a row-dot kernel when absent. Shapes the column-split kernel does not cover (N > 128)
-    take the one-CTA-per-graph kernel."""
+    wrote feat); computed here by a row-dot kernel when absent. Shapes the list kernel does not cover (N > 256, H % 4)
+    take the dense one-CTA-per-graph kernel."""
     lib = _lib.load()
-    _chk_f32(adj, "adj"); _chk_f32(feat, "feat"); _chk_f32(wp, "wp"); _chk_f32(gate, "gate")
+    _chk_f32(feat, "feat"); _chk_f32(wp, "wp"); _chk_f32(gate, "gate")
     G, N, H = feat.shape
-    assert adj.shape == (G, N, N) and adj.is_contiguous() and feat.is_contiguous()
+    assert tuple(adj.shape) == (G, N, N) and feat.is_contiguous()
     assert wp.numel() == H and wp.is_contiguous() and gate.numel() == 12 and gate.is_contiguous()
     score = torch.empty((G, N), dtype=torch.float32, device=feat.device) if want_score else None
     keep = torch.empty((G, N), dtype=torch.uint8, device=feat.device)
     out = alloc_planes(planes_n, G * N, H, feat.device) if planes_n else torch.empty_like(feat)
-    split = int(lib.get_graph_split_slices(N, H)) > 0 and os.environ.get("GET_B200_GRAPH_SPLIT", "0") != "0"
-    if split and sp_parts is None:
+    adj = as_lists(adj)
+    mode = "lists" if adj.usable(H) else "dense"
+    if mode == "dense" and int(lib.get_graph_split_slices(N, H)) > 0 and os.environ.get("GET_B200_GRAPH_SPLIT", "0") != "0":
+        mode = "split"
+    if mode != "dense" and sp_parts is None:
         sp_parts = rowdot(feat.view(G * N, H), wp, drop_p, seed_scorer)
-    if not split:
+    if mode == "dense":
         sp_parts = None
-    rec = (adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF, score, keep, out, sp_parts)
+    rec = (adj, feat, wp, gate, int(k), float(drop_p), seed_scorer & 0xFFFFFFFF, seed_layer2 & 0xFFFFFFFF, score, keep, out, sp_parts,
+           mode)
     if PROFILE_GSL_ARGS is not None:
         PROFILE_GSL_ARGS.append(rec)
     prof = PROFILE_GSL_EVENTS
@@ -484,16 +545,23 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     return score, keep, out
 
 
-def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out, sp_parts=None):
+def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out, sp_parts=None, mode="dense"):
     lib = _lib.load()
     G, N, H = feat.shape
     pl = out if isinstance(out, Planes) else None
-    if sp_parts is not None:
+    plane_args = (None if pl else out.data_ptr(), pl.ptr if pl else None, pl.ld if pl else 0, pl.plane_stride if pl else 0,
+                  pl.nplanes if pl else 0)
+    if mode == "lists":
+        assert sp_parts.is_contiguous() and sp_parts.shape[1] == G * N
+        _lib.check(lib.get_gsl_gather(adj.nbr.data_ptr(), adj.cnt.data_ptr(), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0],
+                                      gate.data_ptr(), G, N, H, k, drop_p, s2, _ptr(score), keep.data_ptr(), *plane_args, _stream()),
+                   "get_gsl_gather")
+        return
+    adj = dense_adj(adj)
+    if mode == "split":
         assert sp_parts.is_contiguous() and sp_parts.shape[1] == G * N
         _lib.check(lib.get_gsl_fused_sp(adj.data_ptr(), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0], gate.data_ptr(), G, N,
-                                        H, k, drop_p, s2, _ptr(score), keep.data_ptr(), None if pl else out.data_ptr(),
-                                        pl.ptr if pl else None, pl.ld if pl else 0, pl.plane_stride if pl else 0,
-                                        pl.nplanes if pl else 0, _stream()), "get_gsl_fused_sp")
+                                        H, k, drop_p, s2, _ptr(score), keep.data_ptr(), *plane_args, _stream()), "get_gsl_fused_sp")
     elif pl is not None:
         _lib.check(lib.get_gsl_fused_bp(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k, drop_p, s1, s2,
                                         _ptr(score), keep.data_ptr(), None, pl.ptr, pl.ld, pl.plane_stride, pl.nplanes,
@@ -600,12 +668,12 @@ class GGNNLayerFn(torch.autograd.Function):
     def forward(ctx, adj, feat, table, ids, keep, pre_agg, p_drop, seed,
                 Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, exact_fwd=False, out_planes=0,
                 rd_w=None, rd_p=0.0, rd_seed=0):
-        G, N = adj.shape[0], adj.shape[1]
+        adj = as_lists(adj)                 # built here when the caller passed a dense adjacency
+        G, N = adj.G, adj.N
         M = G * N
         H, Din = Wp.shape
         Hp = round_up(H + 1, 8)
         dev = adj.device
-        adj = adj.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         mode = gemm_mode(exact_fwd)
         bn = planes.tile_n(M, H, mode)
@@ -644,7 +712,8 @@ class GGNNLayerFn(torch.autograd.Function):
         gemm_bp([(aP, ph.planes.view_cols(0, H), H), (rxP, ph.planes.view_cols(Hp, H), H)], M, H, mode=mode,
                 epilogue=BPE_TANH_BLEND, C=out, out1=h, bias=ph.bias, aux0=z, aux1=x, planes_out=op, tn=bn,
                 rowdot=(rd_w, rd, rd_p, rd_seed) if rd is not None else None)
-        ctx.save_for_backward(adj, keep, xd.t, xar.t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1)
+        ctx.save_for_backward(keep, xd.t, xar.t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1)
+        ctx.adj = adj
         ctx.p_drop, ctx.seed, ctx.dims, ctx.has_feat, ctx.gs = p_drop, seed, (G, N, H, Din), feat is not None, gs
         op_t = op.t if op is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)
         rd_t = rd if rd is not None else torch.empty(0, dtype=torch.float32, device=dev)
@@ -653,7 +722,8 @@ class GGNNLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dplanes, _drd):
-        (adj, keep, xd_t, xar_t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1) = ctx.saved_tensors
+        (keep, xd_t, xar_t, x, z, r, h, Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1) = ctx.saved_tensors
+        adj = ctx.adj
         G, N, H, Din = ctx.dims
         M = G * N
         Hp = round_up(H + 1, 8)
@@ -730,11 +800,11 @@ class GGNNLayerSimtFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, adj, feat, table, ids, keep, pre_agg, p_drop, seed,
                 Wp, Wz0, bz0, Wz1, bz1, Wr0, br0, Wr1, br1, Wh0, bh0, Wh1, bh1, exact_fwd=False):
-        G, N = adj.shape[0], adj.shape[1]
+        adj = as_lists(adj)
+        G, N = adj.G, adj.N
         M = G * N
         H, Din = Wp.shape
         dev = adj.device
-        adj = adj.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         x = torch.empty((M, H), **f32)
         # the projection input (embedding gather and / or dropout) is materialised once: the forward projection and the
@@ -760,13 +830,15 @@ class GGNNLayerSimtFn(torch.autograd.Function):
         gemm([(a, Wz0), (x, Wz1)], z, epilogue=EPI_SIGMOID, bias0=bz0, bias1=bz1)
         gemm([(a, Wr0), (x, Wr1)], r, epilogue=EPI_SIGMOID, bias0=br0, bias1=br1, aux0=x, out1=rx)
         gemm([(a, Wh0), (rx, Wh1)], out, epilogue=EPI_TANH_BLEND, bias0=bh0, bias1=bh1, aux0=z, aux1=x, out1=h)
-        ctx.save_for_backward(adj, xd, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1)
+        ctx.save_for_backward(xd, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1)
+        ctx.adj = adj
         ctx.p_drop, ctx.seed, ctx.dims, ctx.has_feat = p_drop, seed, (G, N, H, Din), feat is not None
         return out.view(G, N, H)
 
     @staticmethod
     def backward(ctx, dout):
-        adj, xd, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1 = ctx.saved_tensors
+        xd, keep, x, a, z, r, rx, h, Wp, Wz0, Wz1, Wr0, Wr1, Wh0, Wh1 = ctx.saved_tensors
+        adj = ctx.adj
         G, N, H, Din = ctx.dims
         M = G * N
         dev = dout.device

@@ -264,6 +264,26 @@ int get_graph_split_slices(int N, int H);
 /* out[m] = dropout(F[m,:]; drop_p, seed, index m*H + c) . w   (the `proj` of GGNN(H -> 1), wrapper.py:191). */
 int get_rowdot_f32(const float* F, const float* w, int64_t M, int H, float drop_p, uint32_t seed, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Packed neighbour lists: the graph path of the model. The dense (G,N,N) adjacency (4-13 % dense) is read ONCE per
+ * step; every aggregation of the step (wrapper.py:192 in both GGNN layers, the scorer's adj @ s_p, and the two adj^T
+ * products of the backward pass) then walks {neighbour index, weight} lists.
+ *   nbr / nbr_t : (G, N, N) entries of 8 bytes {int32 neighbour index, float weight}; the list of row i of graph g starts
+ *                 at entry (g*N + i)*N (capacity N: no overflow case); nbr_t holds the rows of adj^T.
+ *   cnt / cnt_t : (G, N) int32 entries per row.    N <= 232.
+ * ---------------------------------------------------------------------------------------------- */
+int get_build_neighbor_lists(const float* adj, int G, int N, void* nbr, int32_t* cnt, void* nbr_t, int32_t* cnt_t,
+                             void* stream);
+/* out[g,i,:] (+)= sum_e w_e * x[g, j_e, :], edges between two dropped nodes skipped when keep != NULL (same semantics as
+ * get_graph_aggregate_bp; pass nbr_t / cnt_t for the transposed product). out and / or bf16 planes. */
+int get_graph_gather(const void* nbr, const int32_t* cnt, const float* x, const uint8_t* keep, float* out, void* planes,
+                     int64_t ld_p, int64_t plane_stride, int nplanes, int pad_one, int G, int N, int H, int accumulate,
+                     void* stream);
+/* The fused GSL kernel on lists (same outputs and argument meaning as get_gsl_fused_sp). */
+int get_gsl_gather(const void* nbr, const int32_t* cnt, const float* F, const float* sp_parts, int n_sp, const float* gate,
+                   int G, int N, int H, int k, float drop_p, uint32_t seed_layer2, float* score, uint8_t* keep, float* out,
+                   void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
+
 /* GSL.forward as a stand-alone op (wrapper.py:215-227): adj_out = adj * mask(top-k(score)). score (G,N). */
 int get_gsl_mask_adj_f32(const float* adj, const float* score, int G, int N, int k,
                          float* adj_out, uint8_t* keep, void* stream);
