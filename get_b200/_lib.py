@@ -90,9 +90,9 @@ SIGNATURES = {
     "get_gsl_fused_bp": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
     "get_gsl_fused_sp": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _F, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
     "get_graph_split_slices": (_I, [_I, _I]),
-    "get_build_neighbor_lists": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
-    "get_graph_gather": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
-    "get_gsl_gather": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _F, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "get_build_neighbor_lists": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "get_graph_gather": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "get_gsl_gather": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _F, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
     "get_rowdot_f32": (_I, [_P, _P, _L, _I, _F, _U, _P, _P]),
     "get_gsl_mask_adj_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "get_att_pool_fwd_f32": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
@@ -138,8 +138,16 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path):
-        path = _build.build()     # raises RuntimeError when nvcc is unavailable
+    if not _build.is_current():
+        # missing, or built from other sources than the ones next to it: rebuild (raises RuntimeError when nvcc is
+        # unavailable and there is no library at all; a stale library without nvcc is refused rather than loaded)
+        try:
+            path = _build.build()
+        except RuntimeError:
+            if os.path.exists(path):
+                raise RuntimeError("libget_b200.so is stale (sources changed since it was built) and nvcc is not available "
+                                   "to rebuild it: run `python -m get_b200.build` where nvcc exists")
+            raise
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError if the symbol is missing

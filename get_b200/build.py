@@ -28,7 +28,7 @@ def _digest():
     files = _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files.append(os.path.join(os.path.dirname(HERE), "include", "get_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # location-independent: the built library travels with the tree
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -42,7 +42,27 @@ def nvcc_path():
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
 
 
+def is_current() -> bool:
+    """Does the built library match the sources (and nvcc flags) it sits next to?"""
+    try:
+        return os.path.exists(LIB) and open(STAMP).read().strip() == _digest()
+    except OSError:
+        return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if stale or forced) under an exclusive file lock: concurrent ranks / test workers build once, the others
+    wait and pick up the result; the library is linked under a temporary name and renamed into place."""
+    import fcntl
+    with open(os.path.join(CSRC, ".build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB
@@ -62,8 +82,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building get_b200 kernels")
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-lcudart"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB

@@ -439,13 +439,15 @@ class NeighborLists(object):
             self.nbr_t = torch.empty((G, N, N, 2), dtype=torch.float32, device=adj.device)
             self.cnt = torch.empty((G, N), dtype=torch.int32, device=adj.device)
             self.cnt_t = torch.empty((G, N), dtype=torch.int32, device=adj.device)
+            self.used = torch.empty((2, G), dtype=torch.int32, device=adj.device)     # rows any list refers to: [nbr, nbr_t]
             self.rebuild()
 
     def rebuild(self):
         """Re-pack after the dense adjacency changed in place."""
         if self.nbr is not None:
             _lib.check(_lib.load().get_build_neighbor_lists(self.adj.data_ptr(), self.G, self.N, self.nbr.data_ptr(), self.cnt.data_ptr(),
-                                                            self.nbr_t.data_ptr(), self.cnt_t.data_ptr(), _stream()),
+                                                            self.nbr_t.data_ptr(), self.cnt_t.data_ptr(), self.used.data_ptr(),
+                                                            _stream()),
                        "get_build_neighbor_lists")
         return self
 
@@ -477,9 +479,9 @@ def graph_aggregate(adj, x, keep=None, out=None, transpose=False, accumulate=Fal
     if planes_out is not None:
         assert planes_out.rows == G * N and planes_out.cols == H
     if isinstance(adj, NeighborLists) and adj.usable(H):
-        nbr, cnt = (adj.nbr_t, adj.cnt_t) if transpose else (adj.nbr, adj.cnt)
+        nbr, cnt, used = (adj.nbr_t, adj.cnt_t, adj.used[1]) if transpose else (adj.nbr, adj.cnt, adj.used[0])
         pl = planes_out
-        _lib.check(lib.get_graph_gather(nbr.data_ptr(), cnt.data_ptr(), x.data_ptr(), _ptr(keep), _ptr(out), pl.ptr if pl else None,
+        _lib.check(lib.get_graph_gather(nbr.data_ptr(), cnt.data_ptr(), used.data_ptr(), x.data_ptr(), _ptr(keep), _ptr(out), pl.ptr if pl else None,
                                         pl.ld if pl else 0, pl.plane_stride if pl else 0, pl.nplanes if pl else 0, int(pad_one),
                                         G, N, H, int(accumulate), _stream()), "get_graph_gather")
         return out
@@ -553,7 +555,7 @@ def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out, sp_par
                   pl.nplanes if pl else 0)
     if mode == "lists":
         assert sp_parts.is_contiguous() and sp_parts.shape[1] == G * N
-        _lib.check(lib.get_gsl_gather(adj.nbr.data_ptr(), adj.cnt.data_ptr(), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0],
+        _lib.check(lib.get_gsl_gather(adj.nbr.data_ptr(), adj.cnt.data_ptr(), adj.used.data_ptr(), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0],
                                       gate.data_ptr(), G, N, H, k, drop_p, s2, _ptr(score), keep.data_ptr(), *plane_args, _stream()),
                    "get_gsl_gather")
         return

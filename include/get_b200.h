@@ -271,16 +271,20 @@ int get_rowdot_f32(const float* F, const float* w, int64_t M, int H, float drop_
  *   nbr / nbr_t : (G, N, N) entries of 8 bytes {int32 neighbour index, float weight}; the list of row i of graph g starts
  *                 at entry (g*N + i)*N (capacity N: no overflow case); nbr_t holds the rows of adj^T.
  *   cnt / cnt_t : (G, N) int32 entries per row.    N <= 232.
+ *   used        : (2, G) int32: 1 + the highest neighbour index any list of graph g refers to, for nbr ([0]) and nbr_t ([1])
+ *                 -- feature rows at or beyond it (the pad nodes at the end of a text) are never gathered, so the graph
+ *                 kernels neither load nor mask them.
  * ---------------------------------------------------------------------------------------------- */
 int get_build_neighbor_lists(const float* adj, int G, int N, void* nbr, int32_t* cnt, void* nbr_t, int32_t* cnt_t,
-                             void* stream);
+                             int32_t* used, void* stream);
 /* out[g,i,:] (+)= sum_e w_e * x[g, j_e, :], edges between two dropped nodes skipped when keep != NULL (same semantics as
- * get_graph_aggregate_bp; pass nbr_t / cnt_t for the transposed product). out and / or bf16 planes. */
-int get_graph_gather(const void* nbr, const int32_t* cnt, const float* x, const uint8_t* keep, float* out, void* planes,
+ * get_graph_aggregate_bp; pass nbr_t / cnt_t / used + G for the transposed product; used may be NULL). out and / or bf16
+ * planes. */
+int get_graph_gather(const void* nbr, const int32_t* cnt, const int32_t* used, const float* x, const uint8_t* keep, float* out, void* planes,
                      int64_t ld_p, int64_t plane_stride, int nplanes, int pad_one, int G, int N, int H, int accumulate,
                      void* stream);
 /* The fused GSL kernel on lists (same outputs and argument meaning as get_gsl_fused_sp). */
-int get_gsl_gather(const void* nbr, const int32_t* cnt, const float* F, const float* sp_parts, int n_sp, const float* gate,
+int get_gsl_gather(const void* nbr, const int32_t* cnt, const int32_t* used, const float* F, const float* sp_parts, int n_sp, const float* gate,
                    int G, int N, int H, int k, float drop_p, uint32_t seed_layer2, float* score, uint8_t* keep, float* out,
                    void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
 
