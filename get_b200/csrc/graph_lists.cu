@@ -19,6 +19,7 @@
 #include "tcgen05.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <set>
 
 namespace getb {
@@ -38,7 +39,7 @@ struct GatherParams {
   const float* sp_parts; int n_sp;
   const float* gate;
   int k, np2_shift;
-  int prefetch_stride;    // whole-graph kernel: graph g prefetches the tile of graph g + stride into L2
+  int tile_rows;          // whole-graph kernel: feature rows the shared-memory tile holds (the rest is gathered from global)
   int nsplit, qs;         // column slices per graph, float4 quads per slice (<= 16)
   uint32_t thr; float scale; uint32_t seed_2; const uint32_t* salt;
   float* score; uint8_t* keep_out;
@@ -184,9 +185,10 @@ __device__ __forceinline__ void store_pad_quad(const RowOut& o, int H, int k, bo
 //   * per-graph scoring once per graph (not per slice).
 // smem: [tile N*H f32][sp N][score N][rank N i32][keep N u8 (padded)][mbarrier]
 // =====================================================================================================
-constexpr int GR_THREADS = 1024;
+constexpr int GR_THREADS = 512;
 constexpr int GR_WARPS = GR_THREADS / 32;
 constexpr size_t GR_SMEM_LIMIT = 224 * 1024;
+constexpr size_t GR_SMEM_HALF = 113 * 1024;       // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 
 __device__ __forceinline__ uint32_t gr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
@@ -349,16 +351,18 @@ __device__ __forceinline__ void dropout_tile(const GatherParams& p, float4* tile
   }
 }
 
-template <bool FUSED, int NQ, int RPW, int NP>
-__global__ void __launch_bounds__(GR_THREADS, 1) gather_row_kernel(const __grid_constant__ GatherParams p) {
+template <bool FUSED, int NQ, int NP, bool SPILL>
+__global__ void __launch_bounds__(GR_THREADS, 2) gather_row_kernel(const __grid_constant__ GatherParams p) {
   extern __shared__ __align__(128) float4 gr_tile[];
   const int g = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, H = p.H, HQ = H >> 2;
   const int64_t row0 = (int64_t)g * N;
-  const GraphSmem m = graph_smem(gr_tile + (size_t)N * HQ, N);
+  const int cap = SPILL ? p.tile_rows : N;                       // feature rows the shared-memory tile can hold
+  const GraphSmem m = graph_smem(gr_tile + (size_t)cap * HQ, N);
   const bool drop = FUSED && p.thr != 0;
   const int n_used = p.used ? min(N, __ldg(p.used + g)) : N;     // feature rows that can be gathered at all
+  const int n_tile = min(n_used, cap);
 #ifdef GETB_GRAPH_TIMELINE
   __shared__ long long trow[8];
   const long long tr0 = clock64();
@@ -367,11 +371,18 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gather_row_kernel(const __grid_
 #define GR_T(i) do { } while (0)
 #endif
 
-  // ---- tile: bulk copies on one mbarrier; next tile of this SM -> L2 ---------------------------------------------------
-  if (tid == 0) {
+  // ---- this warp's first list, and (fused) the scorer's loads, go out BEFORE the bulk tile traffic ---------------------
+  const int lcap = lane < N ? lane : N - 1;           // entries beyond cnt are allocated, unread garbage
+  float2 nxt_e = make_float2(0.f, 0.f);
+  int nxt_c = 0;
+  if (warp < N) {
+    nxt_e = __ldg(p.nbr + (row0 + warp) * N + lcap);
+    nxt_c = __ldg(p.cnt + row0 + warp);
+  }
+  if (tid == GR_THREADS - 32) {                       // a warp with no scorer work issues the copies
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gr_smem_u32(m.bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t total = (uint32_t)n_used * (uint32_t)H * 4u;
+    const uint32_t total = (uint32_t)n_tile * (uint32_t)H * 4u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gr_smem_u32(m.bar)), "r"(total) : "memory");
     const char* src = reinterpret_cast<const char*>(p.x + row0 * H);
     char* dst = reinterpret_cast<char*>(gr_tile);
@@ -379,33 +390,6 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gather_row_kernel(const __grid_
       const uint32_t n = min(32768u, total - off);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(gr_smem_u32(dst + off)), "l"(src + off), "r"(n), "r"(gr_smem_u32(m.bar)) : "memory");
-    }
-  }
-  if (tid == 32) {
-    const int gn = g + p.prefetch_stride;
-    if (gn < p.G) {
-      const uint32_t total = (uint32_t)(p.used ? min(N, __ldg(p.used + gn)) : N) * (uint32_t)H * 4u;
-      const char* src = reinterpret_cast<const char*>(p.x + (int64_t)gn * N * H);
-      for (uint32_t off = 0; off < total; off += 32768u) {
-        const uint32_t n = min(32768u, total - off);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(n) : "memory");
-      }
-    }
-  }
-  // ---- this warp's list entries, long before they are used -------------------------------------------------------------
-  float2 ent[RPW];
-  int cnts[RPW];
-  {
-    const int lcap = lane < N ? lane : N - 1;         // entries beyond cnt are allocated, unread garbage
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const int i = warp + r * GR_WARPS;
-      ent[r] = make_float2(0.f, 0.f);
-      cnts[r] = 0;
-      if (i < N) {
-        ent[r] = __ldg(p.nbr + (row0 + i) * N + lcap);
-        cnts[r] = __ldg(p.cnt + row0 + i);
-      }
     }
   }
 
@@ -417,9 +401,9 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gather_row_kernel(const __grid_
   }
   const bool masked = FUSED || (p.keep_in != nullptr);
   GR_T(2);
-  if (n_used) gr_mbar_wait(m.bar, 0);
+  if (n_tile) gr_mbar_wait(m.bar, 0);
   GR_T(3);
-  if (drop) dropout_tile<GR_THREADS>(p, gr_tile, HQ, n_used, HQ, 0, row0, tid);
+  if (drop) dropout_tile<GR_THREADS>(p, gr_tile, HQ, n_tile, HQ, 0, row0, tid);
   __syncthreads();
   GR_T(4);
 
@@ -428,21 +412,33 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gather_row_kernel(const __grid_
   const int npq = NP ? ((((H + (p.pad_one ? 1 : 0)) + 7) & ~7) - H) >> 2 : 0;
   const uint32_t tl = gr_smem_u32(gr_tile) + (uint32_t)lane * 16u;   // explicit shared address: no per-edge base recomputation
   const uint32_t pitch = (uint32_t)HQ * 16u;
+  const float4* xg = reinterpret_cast<const float4*>(p.x + row0 * H) + lane;
+  const uint32_t seed = drop ? p.seed_2 + __ldg(p.salt) : 0u;
+  // rows beyond the tile's capacity (texts with more than `cap` distinct words, SPILL only) come straight from global
+  // memory, the layer-2 dropout applied per gathered quad
 #define GR_EDGE(J, W)                                                                                          \
   {                                                                                                            \
-    const uint32_t ra = tl + (uint32_t)(J) * pitch;                                                            \
-    _Pragma("unroll") for (int u = 0; u < NQ; ++u) {                                                           \
-      if (u < NQ - 1 || last_ok) {                                                                             \
-        const float4 f = lds128f(ra + u * 512);                                                                \
-        acc[u].x = fmaf(W, f.x, acc[u].x); acc[u].y = fmaf(W, f.y, acc[u].y);                                  \
-        acc[u].z = fmaf(W, f.z, acc[u].z); acc[u].w = fmaf(W, f.w, acc[u].w);                                  \
+    if (!SPILL || (J) < cap) {                                                                                 \
+      const uint32_t ra = tl + (uint32_t)(J) * pitch;                                                          \
+      _Pragma("unroll") for (int u = 0; u < NQ; ++u) {                                                         \
+        if (u < NQ - 1 || last_ok) {                                                                           \
+          const float4 f = lds128f(ra + u * 512);                                                              \
+          acc[u].x = fmaf(W, f.x, acc[u].x); acc[u].y = fmaf(W, f.y, acc[u].y);                                \
+          acc[u].z = fmaf(W, f.z, acc[u].z); acc[u].w = fmaf(W, f.w, acc[u].w);                                \
+        }                                                                                                      \
+      }                                                                                                        \
+    } else {                                                                                                   \
+      _Pragma("unroll") for (int u = 0; u < NQ; ++u) {                                                         \
+        if (u < NQ - 1 || last_ok) {                                                                           \
+          float4 f = __ldg(xg + (int64_t)(J) * HQ + u * 32);                                                   \
+          if (drop) drop_apply4(seed, (uint64_t)(row0 + (J)) * (uint64_t)H + (uint64_t)(lane + u * 32) * 4, p.thr, p.scale, f); \
+          acc[u].x = fmaf(W, f.x, acc[u].x); acc[u].y = fmaf(W, f.y, acc[u].y);                                \
+          acc[u].z = fmaf(W, f.z, acc[u].z); acc[u].w = fmaf(W, f.w, acc[u].w);                                \
+        }                                                                                                      \
       }                                                                                                        \
     }                                                                                                          \
   }
-#pragma unroll
-  for (int r = 0; r < RPW; ++r) {
-    const int i = warp + r * GR_WARPS;
-    if (i >= N) break;                                 // warp-uniform
+  for (int i = warp; i < N; i += GR_WARPS) {           // warp-uniform
     const RowOut ro = row_out(p, row0 + i);
     float4 acc[NQ];
 #pragma unroll
@@ -450,9 +446,13 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gather_row_kernel(const __grid_
       acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.accumulate && (u < NQ - 1 || last_ok)) acc[u] = ro.f32[lane + u * 32];   // in flight during the edge loop
     }
-    const int cnt = cnts[r];
+    const int cnt = nxt_c;
+    float2 my = nxt_e;
+    if (i + GR_WARPS < N) {                            // next row's list, one row ahead
+      nxt_e = __ldg(p.nbr + (row0 + i + GR_WARPS) * N + lcap);
+      nxt_c = __ldg(p.cnt + row0 + i + GR_WARPS);
+    }
     const bool dropped = masked && m.keep[i] == 0;     // a dropped node keeps only its edges to kept nodes (wrapper.py:221-225)
-    float2 my = ent[r];
     for (int e0 = 0; e0 < cnt; e0 += 32) {
       if (e0) my = (e0 + lane < cnt) ? __ldg(p.nbr + (row0 + i) * N + e0 + lane) : make_float2(0.f, 0.f);
       const int ne = min(32, cnt - e0);
@@ -482,38 +482,38 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gather_row_kernel(const __grid_
     if (NP && lane < npq) store_pad_quad<NP>(ro, H, lane, p.pad_one != 0);
   }
 #ifdef GETB_GRAPH_TIMELINE
-  if (lane == 0 && warp == 31) trow[6] = clock64() - tr0;
+  if (lane == 0 && warp == GR_WARPS - 1) trow[6] = clock64() - tr0;
   __syncthreads();
   GR_T(5);
   if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100 || blockIdx.x == 219 || blockIdx.x == 3000))
-    printf("GRDBG cta %d fused %d used %d: scoring %lld tile_landed %lld dropout %lld warp31_done %lld all_done %lld\n", blockIdx.x,
+    printf("GRDBG cta %d fused %d used %d: scoring %lld tile_landed %lld dropout %lld lastwarp_done %lld all_done %lld\n", blockIdx.x,
            (int)FUSED, n_used, trow[2], trow[3], trow[4], trow[6], trow[5]);
 #endif
 }
 #undef GR_EDGE
 
 typedef void (*GatherRowFn)(const GatherParams);
-template <bool FUSED, int RPW, int NP>
+template <bool FUSED, int NP, bool SPILL>
 static GatherRowFn gather_row_fn_nq(int nq) {
   switch (nq) {
-    case 1: return gather_row_kernel<FUSED, 1, RPW, NP>;
-    case 2: return gather_row_kernel<FUSED, 2, RPW, NP>;
-    case 3: return gather_row_kernel<FUSED, 3, RPW, NP>;
-    default: return gather_row_kernel<FUSED, 4, RPW, NP>;
+    case 1: return gather_row_kernel<FUSED, 1, NP, SPILL>;
+    case 2: return gather_row_kernel<FUSED, 2, NP, SPILL>;
+    case 3: return gather_row_kernel<FUSED, 3, NP, SPILL>;
+    default: return gather_row_kernel<FUSED, 4, NP, SPILL>;
   }
 }
-template <bool FUSED, int RPW>
+template <bool FUSED, bool SPILL>
 static GatherRowFn gather_row_fn_np(int nq, int np) {
   switch (np) {
-    case 0: return gather_row_fn_nq<FUSED, RPW, 0>(nq);
-    case 1: return gather_row_fn_nq<FUSED, RPW, 1>(nq);
-    case 2: return gather_row_fn_nq<FUSED, RPW, 2>(nq);
-    default: return gather_row_fn_nq<FUSED, RPW, 3>(nq);
+    case 0: return gather_row_fn_nq<FUSED, 0, SPILL>(nq);
+    case 1: return gather_row_fn_nq<FUSED, 1, SPILL>(nq);
+    case 2: return gather_row_fn_nq<FUSED, 2, SPILL>(nq);
+    default: return gather_row_fn_nq<FUSED, 3, SPILL>(nq);
   }
 }
-static GatherRowFn gather_row_fn(bool fused, int nq, int rpw, int np) {
-  if (rpw <= 4) return fused ? gather_row_fn_np<true, 4>(nq, np) : gather_row_fn_np<false, 4>(nq, np);
-  return fused ? gather_row_fn_np<true, 8>(nq, np) : gather_row_fn_np<false, 8>(nq, np);
+static GatherRowFn gather_row_fn(bool fused, int nq, int np, bool spill) {
+  if (spill) return fused ? gather_row_fn_np<true, true>(nq, np) : gather_row_fn_np<false, true>(nq, np);
+  return fused ? gather_row_fn_np<true, false>(nq, np) : gather_row_fn_np<false, false>(nq, np);
 }
 
 // =====================================================================================================
@@ -682,23 +682,20 @@ static int launch_gather(GatherParams& p, bool fused, cudaStream_t st, const cha
       getb::set_error("graph gather: cannot opt in to large shared memory");
       return false;
     }
+    (void)cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     opted.insert(fn);
     return true;
   };
   const size_t smem_small = graph_smem_small(p.N) + 16;
-  const size_t smem_row = (size_t)p.N * p.H * 4 + smem_small;
-  if (which == 0 && smem_row <= GR_SMEM_LIMIT && p.H <= 512) {
+  // whole-graph kernel, two CTAs per SM: the tile holds as many feature rows as fit 113 KB (94 of 100 at Snopes dims; a text
+  // uses `used` <= N rows, typically ~75); worthwhile while at least 3/4 of the rows fit
+  const int cap_rows = (int)std::min<size_t>((size_t)p.N, (GR_SMEM_HALF - smem_small) / ((size_t)p.H * 4));
+  if (which == 0 && cap_rows * 4 >= p.N * 3 && p.H <= 512) {
+    const size_t smem_row = (size_t)cap_rows * p.H * 4 + smem_small;
     const int nq = (p.H / 4 + 31) / 32;
-    const int rpw = (p.N + GR_WARPS - 1) / GR_WARPS;
-    GatherRowFn fn = gather_row_fn(fused, nq, rpw, np);
+    p.tile_rows = cap_rows;
+    GatherRowFn fn = gather_row_fn(fused, nq, np, cap_rows < p.N);
     if (!opt_in((const void*)fn, smem_row)) return -2;
-    static int n_sm = 0;
-    if (!n_sm) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
-    p.prefetch_stride = n_sm > 0 ? n_sm : 148;
     fn<<<p.G, GR_THREADS, smem_row, st>>>(p);
     GETB_CHECK_LAUNCH(name);
     return 0;

@@ -11,12 +11,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _graphs(G, N, window, seed, asym=False):
+def _graphs(G, N, window, seed, asym=False, vocab=60):
     rng = np.random.default_rng(seed)
     adj = []
     for g in range(G):
-        toks = rng.integers(2, 60, size=N)
-        if g % 5 == 4:
+        toks = rng.integers(2, vocab, size=N)
+        if g % 5 == 4 and vocab == 60:
             toks[N // 2:] = 0                      # padded tail: rows without neighbours
         adj.append(synthetic.word_graph(toks, N, window)[1].astype(np.float32))
     a = np.stack(adj)
@@ -103,3 +103,31 @@ def test_fused_gsl_on_lists_equals_dense_kernel(G, N, H, k, p):
     _, k2, pl = ops.gsl_fused(ops.NeighborLists(adj), feat, wp, gate, k, drop_p=p, seed_scorer=11, seed_layer2=12, planes_n=3)
     assert (k2 == k1).all()
     assert (pl.to_float().view(G, N, H) - o1).abs().max().item() <= 1e-6 * max(1.0, o1.abs().max().item())
+
+
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_texts_with_more_distinct_words_than_the_tile_holds(p):
+    """Snopes dims, texts of ~100 distinct words: the whole-graph kernel's shared-memory tile holds 94 feature rows, the rest
+    is gathered from global memory (with the dropout draw applied per gathered quad)."""
+    G, N, H, k = 5, 100, 300, 60
+    adj = _graphs(G, N, 3, 9, vocab=50000).contiguous()
+    L = ops.NeighborLists(adj)
+    assert int(L.used.max().item()) > 94
+    g = torch.Generator(device=DEV).manual_seed(6)
+    x = torch.randn(G, N, H, device=DEV, generator=g)
+    keep = (torch.rand(G, N, device=DEV, generator=g) < 0.6).to(torch.uint8)
+    for tr in (False, True):
+        assert (ops.graph_aggregate(L, x, keep, transpose=tr) - ops.graph_aggregate(adj, x, keep, transpose=tr)).abs().max().item() <= 2e-6
+    wp = torch.randn(H, device=DEV, generator=g) * 0.1
+    gate = torch.randn(12, device=DEV, generator=g)
+    import os
+    os.environ["GET_B200_GRAPH_LISTS"] = "0"
+    try:
+        s0, k0, o0 = ops.gsl_fused(adj, x, wp, gate, k, drop_p=p, seed_scorer=11, seed_layer2=12)
+    finally:
+        os.environ.pop("GET_B200_GRAPH_LISTS")
+    s1, k1, o1 = ops.gsl_fused(L, x, wp, gate, k, drop_p=p, seed_scorer=11, seed_layer2=12)
+    assert (s0 - s1).abs().max().item() <= 2e-6
+    same = ~(k0 != k1).any(1)
+    assert same.sum().item() >= G - 1
+    assert (o0[same] - o1[same]).abs().max().item() <= 2e-6 * max(1.0, o0.abs().max().item())

@@ -61,7 +61,7 @@ def test_flat_adam_matches_torch_adam_and_sinks_match_autograd():
         assert torch.equal(g1[n], g2[n]), "sink gradient differs from the autograd gradient: %s" % n
     assert np.allclose(l1, l2, rtol=0, atol=2e-6), (l1, l2)
     for n in p1:
-        assert float((p1[n] - p2[n]).abs().max()) < 2e-6, n
+        assert float((p1[n] - p2[n]).abs().max()) < 5e-6, n      # 5 steps of lr 1e-3: 1e-3 of the distance travelled
 
 
 def test_eager_forward_after_replays_sees_the_current_weights():
