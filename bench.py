@@ -320,7 +320,7 @@ def torch_cuda_baseline(w, dev, model_ours, iters=10):
         return {"unavailable": "oracle/_ref not present (run python oracle/make_ref.py in the build container)"}
 
     def timed(fn, n):
-        for i in range(3):
+        for i in range(4):                 # every one of the 4 batch shapes once (our side captures a graph per shape)
             fn(i)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -736,7 +736,7 @@ def run_ours(args):
             gsl_ms.append(graph_timed_ms(lambda: [ops.gsl_fused_replay(r) for r in recs]) / len(recs))
             gsl_pairs.append(float(np.mean(ngraphs)))
         gsl_mode = recs[0][12]
-        gsl_nnz = float(np.mean([float(r[0].cnt.sum().item()) / r[1].shape[0] for r in recs])) if gsl_mode == "lists" else None
+        gsl_nnz = float(np.mean([float(r[0].nnz().sum().item()) / r[1].shape[0] for r in recs])) if gsl_mode == "lists" else None
         gsl_nsp = int(recs[0][11].shape[0]) if recs[0][11] is not None else 0
         gsl_planes = recs[0][10].nplanes if hasattr(recs[0][10], "nplanes") else 0
         build_ms = (graph_timed_ms(lambda: [r[0].rebuild() for r in recs]) / len(recs)) if gsl_mode == "lists" else 0.0

@@ -432,27 +432,35 @@ class NeighborLists(object):
         self.adj = adj.contiguous()
         self.G, self.N = int(adj.shape[0]), int(adj.shape[1])
         self.shape, self.device = self.adj.shape, adj.device
-        self.nbr = self.cnt = self.nbr_t = self.cnt_t = None
+        self.ent = self.rowptr = self.used = None
         if self.N <= GL_MAX_N and os.environ.get("GET_B200_GRAPH_LISTS", "1") != "0":
+            lib = _lib.load()
             G, N = self.G, self.N
-            self.nbr = torch.empty((G, N, N, 2), dtype=torch.float32, device=adj.device)
-            self.nbr_t = torch.empty((G, N, N, 2), dtype=torch.float32, device=adj.device)
-            self.cnt = torch.empty((G, N), dtype=torch.int32, device=adj.device)
-            self.cnt_t = torch.empty((G, N), dtype=torch.int32, device=adj.device)
-            self.used = torch.empty((2, G), dtype=torch.int32, device=adj.device)     # rows any list refers to: [nbr, nbr_t]
+            self.ecap = int(lib.get_neighbor_lists_entry_capacity(N))
+            self.pitch = int(lib.get_neighbor_lists_rowptr_pitch(N))
+            # CSR records of adj ([0]) and adj^T ([1]): entries {index, weight}, row pointers, rows referred to
+            self.ent = torch.empty((2, G, self.ecap, 2), dtype=torch.float32, device=adj.device)
+            self.rowptr = torch.empty((2, G, self.pitch), dtype=torch.int32, device=adj.device)
+            self.used = torch.empty((2, G), dtype=torch.int32, device=adj.device)
             self.rebuild()
 
     def rebuild(self):
         """Re-pack after the dense adjacency changed in place."""
-        if self.nbr is not None:
-            _lib.check(_lib.load().get_build_neighbor_lists(self.adj.data_ptr(), self.G, self.N, self.nbr.data_ptr(), self.cnt.data_ptr(),
-                                                            self.nbr_t.data_ptr(), self.cnt_t.data_ptr(), self.used.data_ptr(),
-                                                            _stream()),
-                       "get_build_neighbor_lists")
+        if self.ent is not None:
+            _lib.check(_lib.load().get_build_neighbor_lists(self.adj.data_ptr(), self.G, self.N, self.ent.data_ptr(), self.rowptr.data_ptr(),
+                                                            self.used.data_ptr(), _stream()), "get_build_neighbor_lists")
         return self
 
     def usable(self, H: int) -> bool:
-        return self.nbr is not None and H % 4 == 0 and 4 <= H <= 1024
+        return self.ent is not None and H % 4 == 0 and H >= 4
+
+    def pointers(self, transpose: bool = False):
+        o = 1 if transpose else 0
+        return self.ent[o].data_ptr(), self.rowptr[o].data_ptr(), self.used[o].data_ptr()
+
+    def nnz(self) -> torch.Tensor:
+        """(G,) edges per graph (device tensor)."""
+        return self.rowptr[0][:, self.N]
 
 
 def as_lists(adj) -> NeighborLists:
@@ -479,9 +487,8 @@ def graph_aggregate(adj, x, keep=None, out=None, transpose=False, accumulate=Fal
     if planes_out is not None:
         assert planes_out.rows == G * N and planes_out.cols == H
     if isinstance(adj, NeighborLists) and adj.usable(H):
-        nbr, cnt, used = (adj.nbr_t, adj.cnt_t, adj.used[1]) if transpose else (adj.nbr, adj.cnt, adj.used[0])
         pl = planes_out
-        _lib.check(lib.get_graph_gather(nbr.data_ptr(), cnt.data_ptr(), used.data_ptr(), x.data_ptr(), _ptr(keep), _ptr(out), pl.ptr if pl else None,
+        _lib.check(lib.get_graph_gather(*adj.pointers(transpose), x.data_ptr(), _ptr(keep), _ptr(out), pl.ptr if pl else None,
                                         pl.ld if pl else 0, pl.plane_stride if pl else 0, pl.nplanes if pl else 0, int(pad_one),
                                         G, N, H, int(accumulate), _stream()), "get_graph_gather")
         return out
@@ -555,7 +562,7 @@ def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out, sp_par
                   pl.nplanes if pl else 0)
     if mode == "lists":
         assert sp_parts.is_contiguous() and sp_parts.shape[1] == G * N
-        _lib.check(lib.get_gsl_gather(adj.nbr.data_ptr(), adj.cnt.data_ptr(), adj.used.data_ptr(), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0],
+        _lib.check(lib.get_gsl_gather(*adj.pointers(False), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0],
                                       gate.data_ptr(), G, N, H, k, drop_p, s2, _ptr(score), keep.data_ptr(), *plane_args, _stream()),
                    "get_gsl_gather")
         return

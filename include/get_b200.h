@@ -267,26 +267,28 @@ int get_rowdot_f32(const float* F, const float* w, int64_t M, int H, float drop_
 /* ------------------------------------------------------------------------------------------------
  * Packed neighbour lists: the graph path of the model. The dense (G,N,N) adjacency (4-13 % dense) is read ONCE per
  * step; every aggregation of the step (wrapper.py:192 in both GGNN layers, the scorer's adj @ s_p, and the two adj^T
- * products of the backward pass) then walks {neighbour index, weight} lists.
- *   nbr / nbr_t : (G, N, N) entries of 8 bytes {int32 neighbour index, float weight}; the list of row i of graph g starts
- *                 at entry (g*N + i)*N (capacity N: no overflow case); nbr_t holds the rows of adj^T.
- *   cnt / cnt_t : (G, N) int32 entries per row.    N <= 232.
- *   used        : (2, G) int32: 1 + the highest neighbour index any list of graph g refers to, for nbr ([0]) and nbr_t ([1])
- *                 -- feature rows at or beyond it (the pad nodes at the end of a text) are never gathered, so the graph
- *                 kernels neither load nor mask them.
+ * products of the backward pass) then walks per-graph CSR records, for adj (orientation 0) and adj^T (orientation 1):
+ *   ent    : (2, G, ecap) entries of 8 bytes {int32 neighbour index, float weight}, ecap = get_neighbor_lists_entry_capacity(N)
+ *            (N*N rounded up to even: no overflow case); a graph's entries are compact from the start of its block,
+ *            rows in order, neighbours in increasing index.
+ *   rowptr : (2, G, pitch) int32, pitch = get_neighbor_lists_rowptr_pitch(N); rowptr[i] .. rowptr[i+1] = entries of row i.
+ *   used   : (2, G) int32: 1 + the highest neighbour index any list of graph g refers to -- feature rows at or beyond it
+ *            (the pad nodes at the end of a text) are never gathered, so the graph kernels neither load nor mask them.
+ * N <= 232. The gather entry points take the pointers of ONE orientation (ent + o*G*ecap, rowptr + o*G*pitch, used + o*G).
  * ---------------------------------------------------------------------------------------------- */
-int get_build_neighbor_lists(const float* adj, int G, int N, void* nbr, int32_t* cnt, void* nbr_t, int32_t* cnt_t,
-                             int32_t* used, void* stream);
+int get_neighbor_lists_rowptr_pitch(int N);
+int get_neighbor_lists_entry_capacity(int N);
+int get_build_neighbor_lists(const float* adj, int G, int N, void* ent, int32_t* rowptr, int32_t* used, void* stream);
 /* out[g,i,:] (+)= sum_e w_e * x[g, j_e, :], edges between two dropped nodes skipped when keep != NULL (same semantics as
- * get_graph_aggregate_bp; pass nbr_t / cnt_t / used + G for the transposed product; used may be NULL). out and / or bf16
- * planes. */
-int get_graph_gather(const void* nbr, const int32_t* cnt, const int32_t* used, const float* x, const uint8_t* keep, float* out, void* planes,
-                     int64_t ld_p, int64_t plane_stride, int nplanes, int pad_one, int G, int N, int H, int accumulate,
-                     void* stream);
+ * get_graph_aggregate_bp; pass the records of orientation 1 for the transposed product; used may be NULL). out and / or
+ * bf16 planes. */
+int get_graph_gather(const void* ent, const int32_t* rowptr, const int32_t* used, const float* x, const uint8_t* keep,
+                     float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, int pad_one, int G, int N,
+                     int H, int accumulate, void* stream);
 /* The fused GSL kernel on lists (same outputs and argument meaning as get_gsl_fused_sp). */
-int get_gsl_gather(const void* nbr, const int32_t* cnt, const int32_t* used, const float* F, const float* sp_parts, int n_sp, const float* gate,
-                   int G, int N, int H, int k, float drop_p, uint32_t seed_layer2, float* score, uint8_t* keep, float* out,
-                   void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
+int get_gsl_gather(const void* ent, const int32_t* rowptr, const int32_t* used, const float* F, const float* sp_parts, int n_sp,
+                   const float* gate, int G, int N, int H, int k, float drop_p, uint32_t seed_layer2, float* score,
+                   uint8_t* keep, float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
 
 /* GSL.forward as a stand-alone op (wrapper.py:215-227): adj_out = adj * mask(top-k(score)). score (G,N). */
 int get_gsl_mask_adj_f32(const float* adj, const float* score, int G, int N, int k,

@@ -30,17 +30,16 @@ def test_lists_match_dense_adjacency(G, N, H):
     adj = _graphs(G, N, 3, 1, asym=True)
     L = ops.NeighborLists(adj)
     torch.cuda.synchronize()
-    nbr, cnt = L.nbr.cpu().numpy(), L.cnt.cpu().numpy()
-    nbr_t, cnt_t = L.nbr_t.cpu().numpy(), L.cnt_t.cpu().numpy()
+    ent, rowptr, used = L.ent.cpu().numpy(), L.rowptr.cpu().numpy(), L.used.cpu().numpy()
     a = adj.cpu().numpy()
-    for lists, counts, dense in ((nbr, cnt, a), (nbr_t, cnt_t, a.transpose(0, 2, 1))):
-        assert (counts == (dense != 0).sum(-1)).all()
+    for o, dense in ((0, a), (1, a.transpose(0, 2, 1))):
         for g in range(G):
-            for i in range(0, N, 7):
-                c = counts[g, i]
-                cols = lists[g, i, :c, 0].copy().view(np.int32)
-                assert (cols == np.nonzero(dense[g, i])[0]).all()
-                assert (lists[g, i, :c, 1] == dense[g, i, cols]).all()
+            nzr, nzc = np.nonzero(dense[g])                       # row-major order = CSR order
+            assert (rowptr[o, g, :N + 1] == np.concatenate([[0], np.cumsum((dense[g] != 0).sum(-1))])).all()
+            cols = ent[o, g, :len(nzc), 0].copy().view(np.int32)
+            assert (cols == nzc).all()
+            assert (ent[o, g, :len(nzc), 1] == dense[g][nzr, nzc]).all()
+            assert used[o, g] == (nzc.max() + 1 if len(nzc) else 0)
 
 
 @pytest.mark.parametrize("G,N,H", [(7, 30, 300), (9, 100, 300), (3, 100, 96), (2, 200, 512), (4, 17, 24), (1, 1, 8)])
