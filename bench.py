@@ -805,7 +805,8 @@ def run_ours(args):
                     "precision_note": {"fp32": "16-bit bf16-plane operands (3 tensor-core products), fp32-exact class (6 products) on the GSL top-k chain",
                                        "fp32x": "fp32-exact class everywhere", "bf16": "plain bf16 operands, fp32-exact class on the GSL top-k chain"}[args.precision],
                     "mean_pairs_per_step_per_gpu": pairs / args.steps / world,
-                    "grad_allreduce_bytes": reducer.nbytes if world > 1 else 0, "grad_allreduce": "3 chunks overlapped with the backward pass" if world > 1 else None,
+                    "grad_allreduce_bytes": reducer.nbytes if world > 1 else 0, "grad_allreduce": (("one all-reduce after the backward pass (GET_B200_NO_OVERLAP=1)" if os.environ.get("GET_B200_NO_OVERLAP") == "1"
+                                                                 else "3 chunks overlapped with the backward pass") if world > 1 else None),
                     "claims_sharding": "global batch of %d claims sharded by evidence count" % (w.batch_claims * world) if world > 1 else None,
                     "rank_spread": rank_spread, "wall_s_timed_region": t_wall, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps,
                     "optimizer": "torch.optim.Adam(fused)" if args.torch_adam else "get_adam_flat_f32 (one kernel over the flat bucket)"},

@@ -68,20 +68,30 @@ class FlatGradAllReduce(object):
             names = [names[i] for i in order]
         self.params, self.names = params, names
         self.group = process_group
-        numel = sum(p.numel() for p in self.params)
+        # chunks start on 128-byte boundaries (collectives and vectorised kernels on a chunk see an aligned buffer); the
+        # padding floats stay zero for ever: zero gradient, zero parameter, zero Adam update
+        ALIGN = 32
+        offs, off, prev = [], 0, None
+        for i, p in enumerate(self.params):
+            c = chunk_of(names[i]) if names is not None else 0
+            if prev is not None and c != prev:
+                off = (off + ALIGN - 1) // ALIGN * ALIGN
+            offs.append(off)
+            off += p.numel()
+            prev = c
+        numel = (off + ALIGN - 1) // ALIGN * ALIGN
         dev = self.params[0].device
         self.flat = torch.zeros((numel,), dtype=torch.float32, device=dev)
-        self.views, self.bounds = [], []
-        off = 0
+        self.views, self.bounds, self.offsets = [], [], offs
         chunk_lo = [None] * N_CHUNKS
         chunk_hi = [0] * N_CHUNKS
         for i, p in enumerate(self.params):
+            off = offs[i]
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             c = chunk_of(names[i]) if names is not None else 0
             if chunk_lo[c] is None:
                 chunk_lo[c] = off
             chunk_hi[c] = off + p.numel()
-            off += p.numel()
         self.chunks = [(lo, hi) for lo, hi in zip(chunk_lo, chunk_hi) if lo is not None]
         self._chunk_index = {c: k for k, c in enumerate(c for c in range(N_CHUNKS) if chunk_lo[c] is not None)}
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
@@ -211,14 +221,12 @@ class FlatAdam(object):
                  weight_decay: float = 0.0):
         self.reducer = reducer
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
-        flat = torch.empty_like(reducer.flat)
-        off = 0
+        flat = torch.zeros_like(reducer.flat)
         with torch.no_grad():
-            for p in reducer.params:
+            for p, off in zip(reducer.params, reducer.offsets):
                 v = flat[off:off + p.numel()].view_as(p)
                 v.copy_(p)
                 p.data = v
-                off += p.numel()
         self.flat_param = flat
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)

@@ -135,6 +135,7 @@ class WeightPack(object):
 _packs: Dict[Tuple, WeightPack] = {}
 _pack_epoch = 0
 _pack_table = None        # (device uint8 tensor of get_pack_job[], n_jobs, total_blocks, [packs]) or None when stale
+_retired_tables = []      # superseded job tables, kept alive for the graphs that captured them
 _PACK_MAX = 1024
 
 
@@ -211,8 +212,11 @@ def get_pack(key, build) -> WeightPack:
         _run_jobs(js, blk)
         pk.state = (pk.versions(), _pack_epoch)
         _packs[key] = pk
-        if len(_packs) > _PACK_MAX:
-            _packs.pop(next(iter(_packs)))
+        # Packs and job tables are never freed: captured CUDA graphs hold their device addresses (a graph captured before
+        # this pack existed keeps replaying with the table it was captured with). The number of distinct packs is bounded by
+        # (#weights x #tile configurations).
+        if _pack_table is not None:
+            _retired_tables.append(_pack_table)
         _pack_table = None
         return pk
     if pk.state == (pk.versions(), _pack_epoch):

@@ -13,6 +13,7 @@ gradients are unchanged (every claim is independent of the others, SURVEY.md sec
 Dropout: a replay repeats the captured kernel arguments, so the per-step variation of the masks comes from the
 library's device salt word, advanced by the first node of the graph (include/get_b200.h, get_dropout_salt_advance).
 """
+import os
 import copy
 from typing import Dict, Optional, Tuple
 
@@ -152,6 +153,8 @@ class CapturedTrainStep(object):
         assert not accumulate or (reducer is not None and optimizer is None)
         # collective_in_graph=False: the graph ends after the backward pass (gradients gathered in the flat bucket); the
         # all-reduce and the optimizer step are then issued eagerly after every replay
+        if os.environ.get("GET_B200_SPLIT_TAIL", "0") == "1":
+            collective_in_graph = False
         self.split_tail = (not collective_in_graph) and reducer is not None and reducer.world > 1
         self.loss_fn = loss_fn or ops.cross_entropy
         self.slots: Dict[Tuple, _Slot] = {}
@@ -172,19 +175,23 @@ class CapturedTrainStep(object):
         red = self.reducer
         in_step = collective and not self.split_tail and not self.accumulate
         if red is not None:
-            red.overlap = in_step              # chunk all-reduces are issued from the backward pass
+            # chunk all-reduces are issued from the backward pass (GET_B200_NO_OVERLAP=1: one all-reduce after it, for A/B runs)
+            red.overlap = in_step and os.environ.get("GET_B200_NO_OVERLAP", "0") != "1"
             # the local loss is a mean over the LOCAL claims: re-weight unequal shards
             red.set_weight(s.n_real * red.world / s.global_claims if (s.global_claims and red.world > 1) else 1.0)
         logits = self.model(s.query, s.document, **s.kw)
         loss = self.loss_fn(logits[:s.n_real], s.labels[:s.n_real])
         (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
+        # detached: a slot must not keep the autograd graph alive across steps -- a live graph pins the parameters'
+        # AccumulateGrad nodes to the stream they were created on (an earlier capture / warm-up stream), and the next
+        # capture then forks into that stale stream
         if self.accumulate:
-            return logits, loss
+            return logits.detach(), loss.detach()
         if red is not None:
             red.reduce(collective=in_step)
         if self.optimizer is not None and not self.split_tail:
             self.optimizer.step()
-        return logits, loss
+        return logits.detach(), loss.detach()
 
     def _tail(self):
         """all-reduce + optimizer step outside the graph (collective_in_graph=False)."""
@@ -222,7 +229,9 @@ class CapturedTrainStep(object):
         salt = ops.dropout_salt_get()
         bucket_backup = self.reducer.flat.clone() if self.accumulate else None
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        if getattr(self, "_warm_stream", None) is None:
+            self._warm_stream = torch.cuda.Stream()       # ONE warm-up stream for all builds (streams come from a small pool)
+        side = self._warm_stream
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             if not self.accumulate:
@@ -260,7 +269,12 @@ class CapturedTrainStep(object):
         prof, ops.PROFILE_GSL_EVENTS = ops.PROFILE_GSL_EVENTS, None
         g = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(g):
+        # other threads of a multi-GPU process (the NCCL watchdog polls its events) must not invalidate the capture
+        multi = self.reducer is not None and self.reducer.world > 1
+        if multi:
+            torch.cuda.synchronize()
+        mode = os.environ.get("GET_B200_CAPTURE_MODE", "thread_local" if multi else "global")
+        with torch.cuda.graph(g, capture_error_mode=mode):
             ops.begin_step_capture()
             ops.dropout_salt_advance()
             if self.reducer is not None and self.reducer.attached and not self.accumulate:
