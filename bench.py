@@ -558,10 +558,13 @@ def run_ours(args):
     model, reducer, opt, stepper = build_trainer(w, dev, args.precision, use_graph=use_graph, flat_adam=not args.torch_adam)
 
     # every rank generates the same GLOBAL batches (world x 32 claims) and takes its claim shard, balanced by evidence count
-    from get_b200.step_graph import pad_batch, slice_batch
+    from get_b200.ddp import balance_claims
+    from get_b200.step_graph import pad_batch, select_claims
     glob = make_batches(w, NBATCH, 123756, n_claims=w.batch_claims * world)
-    bounds = [shard_claims(g[K.EvidenceCountPerQuery], world)[rank] for g in glob]
-    batches = [slice_batch(g, lo, hi) for g, (lo, hi) in zip(glob, bounds)]
+    if world > 1:
+        batches = [select_claims(g, balance_claims(g[K.EvidenceCountPerQuery], world)[rank]) for g in glob]
+    else:
+        batches = glob[:]
     gclaims = [g["query"].shape[0] if world > 1 else 0 for g in glob]
     del glob
     padded = [pad_batch(b, PAD_PAIRS) for b in batches] if use_graph else batches
@@ -807,7 +810,8 @@ def run_ours(args):
                     "mean_pairs_per_step_per_gpu": pairs / args.steps / world,
                     "grad_allreduce_bytes": reducer.nbytes if world > 1 else 0, "grad_allreduce": (("one all-reduce after the backward pass (GET_B200_NO_OVERLAP=1)" if os.environ.get("GET_B200_NO_OVERLAP") == "1"
                                                                  else "3 chunks overlapped with the backward pass") if world > 1 else None),
-                    "claims_sharding": "global batch of %d claims sharded by evidence count" % (w.batch_claims * world) if world > 1 else None,
+                    "claims_sharding": ("global batch of %d claims per step, claims dealt to ranks by decreasing evidence count (least-loaded rank first)"
+                                        % (w.batch_claims * world)) if world > 1 else None,
                     "rank_spread": rank_spread, "wall_s_timed_region": t_wall, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps,
                     "optimizer": "torch.optim.Adam(fused)" if args.torch_adam else "get_adam_flat_f32 (one kernel over the flat bucket)"},
             "clocks": clocks,

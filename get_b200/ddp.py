@@ -55,6 +55,21 @@ def shard_claims(evd_cnt, world_size: int):
     return bounds
 
 
+def balance_claims(evd_cnt, world_size: int):
+    """Claims per rank (lists of claim indices, each sorted) balanced by evidence count AND claim count: claims in order
+    of decreasing evidence count go to the rank with the fewest evidences so far (ties: fewest claims, lowest rank). The
+    per-rank evidence totals then differ by at most one claim's worth of the SMALLEST claims, typically 0-1 pairs, where
+    a contiguous split (shard_claims) is off by up to one whole claim."""
+    cnt = [int(c) for c in evd_cnt]
+    order = sorted(range(len(cnt)), key=lambda i: (-cnt[i], i))
+    load, parts = [0] * world_size, [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], len(parts[k]), k))
+        parts[r].append(i)
+        load[r] += cnt[i]
+    return [sorted(p) for p in parts]
+
+
 class FlatGradAllReduce(object):
     """Flat-bucket gradient averaging. `params` = the grad-receiving parameters; `names` (optional, same order) places
     them in backward-completion order so that the bucket can be reduced in chunks that overlap the backward pass."""

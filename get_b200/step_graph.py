@@ -96,6 +96,26 @@ def slice_batch(batch: Dict, lo: int, hi: int) -> Dict:
     return out
 
 
+def select_claims(batch: Dict, claims) -> Dict:
+    """The claims `claims` (any subset, any order) of a numpy mini-batch in the fitter's flattened layout: per-claim arrays
+    are gathered by claim, the flattened evidence arrays by the evidence rows of those claims (a mini-batch is a SET of
+    claims: the mean loss and its gradient do not depend on the order)."""
+    claims = np.asarray(claims, dtype=np.int64)
+    cnt = np.asarray(batch[K.EvidenceCountPerQuery]).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(cnt)])
+    rows = np.concatenate([np.arange(off[c], off[c + 1]) for c in claims]) if len(claims) else np.zeros((0,), np.int64)
+    out = dict(batch)
+    for k in ("query", "document", "labels", K.Query_lens, K.Query_Adj, K.QuerySources, K.DocSources, K.Doc_lens,
+              K.EvidenceCountPerQuery, "raw_query_tokens", "raw_query_lens"):
+        if k in batch:
+            out[k] = batch[k][claims]
+    for k in (K.DocContentNoPaddingEvidence, K.Evd_Docs_Adj, "e_lens", "raw_doc_tokens", "raw_doc_lens"):
+        if k in batch:
+            out[k] = batch[k][rows]
+    out["pairs"] = int(len(rows))
+    return out
+
+
 def token_batch_to_host(batch: Dict, pin: bool = True):
     """The compact host-side form of a mini-batch: raw token ids + counts + sources + labels, a few
     hundred kB instead of the 18.8 MB of dense float64 adjacencies. Returns a dict of (pinned) CPU tensors."""

@@ -21,9 +21,9 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .ddp import FlatAdam, FlatGradAllReduce, shard_claims, trainable_named_parameters
+from .ddp import FlatAdam, FlatGradAllReduce, balance_claims, trainable_named_parameters
 from .keywords import KeyWordSettings as K
-from .step_graph import CapturedTrainStep, pad_batch, slice_batch
+from .step_graph import CapturedTrainStep, pad_batch, select_claims
 
 
 def classification_metrics(labels: Sequence[int], preds: Sequence[int], probs: Sequence[float]) -> Dict[str, float]:
@@ -79,8 +79,8 @@ class GETTrainer(object):
         local loss (device scalar)."""
         from . import synthetic
         B = int(batch["query"].shape[0])
-        lo, hi = shard_claims(batch[K.EvidenceCountPerQuery], self.world)[self.rank] if self.world > 1 else (0, B)
-        local = pad_batch(slice_batch(batch, lo, hi), self.pad_pairs_to)
+        mine = balance_claims(batch[K.EvidenceCountPerQuery], self.world)[self.rank] if self.world > 1 else list(range(B))
+        local = pad_batch(select_claims(batch, mine), self.pad_pairs_to)
         q, d, l, kw = synthetic.batch_to_torch(local, device="cpu", pin=True)
         return self.stepper.step(q, d, l, kw, local["n_real_claims"], global_claims=B if self.world > 1 else 0)
 

@@ -4,14 +4,13 @@
 OUT=gpurun_out
 N=${1:-2}
 mkdir -p $OUT
-timeout 90 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29501 scripts/nccl_align.py 2>&1 | grep "slice" | head -8
-timeout 240 python -m pytest tests/test_gpu_trainer.py -m gpu -q --tb=short -p no:cacheprovider -k two_gpu > $OUT/tests_multi_n$N.log 2>&1; tail -3 $OUT/tests_multi_n$N.log | cut -c1-200
-timeout 200 python bench.py --quick --steps 30 --warmup 5 > $OUT/bench_n1_same_box.json 2> $OUT/bench_n1_same_box.err
+timeout 200 python -m pytest tests/test_gpu_trainer.py -m gpu -q --tb=short -p no:cacheprovider -k two_gpu > $OUT/tests_multi_n$N.log 2>&1; tail -3 $OUT/tests_multi_n$N.log | cut -c1-200
+timeout 150 python bench.py --quick --steps 30 --warmup 5 > $OUT/bench_n1_same_box.json 2> $OUT/bench_n1_same_box.err
 for M in 2 4 8; do
   if [ $M -le $N ]; then
-    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $M --master-addr 127.0.0.1 --master-port $((29510+M)) bench.py --quick --gpus $M --steps 30 --warmup 5 > $OUT/bench_n$M.json 2> $OUT/bench_n$M.err
+    timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $M --master-addr 127.0.0.1 --master-port $((29510+M)) bench.py --quick --gpus $M --steps 30 --warmup 5 > $OUT/bench_n$M.json 2> $OUT/bench_n$M.err
     echo "N=$M exit $? lines $(wc -l < $OUT/bench_n$M.json)"; grep -v "Warn\|warn\|^\*\|OMP_NUM" $OUT/bench_n$M.err | grep "Error\|error" | head -3 | cut -c1-300
-    GET_B200_NO_OVERLAP=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $M --master-addr 127.0.0.1 --master-port $((29520+M)) bench.py --quick --gpus $M --steps 30 --warmup 5 > $OUT/bench_n${M}_no_overlap.json 2> $OUT/bench_n${M}_no_overlap.err
+    GET_B200_NO_OVERLAP=1 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $M --master-addr 127.0.0.1 --master-port $((29520+M)) bench.py --quick --gpus $M --steps 30 --warmup 5 > $OUT/bench_n${M}_no_overlap.json 2> $OUT/bench_n${M}_no_overlap.err
   fi
 done
 python - <<'PY'

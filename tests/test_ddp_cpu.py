@@ -216,3 +216,31 @@ def test_classification_metrics_match_sklearn():
     assert abs(m["f1_micro"] - sk.f1_score(y, p, average="micro")) < 1e-12
     assert abs(m["precision_true_cls"] - sk.precision_score(y, p, labels=[1], average=None)[0]) < 1e-12
     assert abs(m["recall_false_cls"] - sk.recall_score(y, p, labels=[0], average=None)[0]) < 1e-12
+
+
+def test_balanced_claim_assignment_and_selection():
+    """balance_claims: a partition of the claims whose per-rank evidence totals differ by less than the largest claim of the
+    lightest tail; select_claims gathers exactly those claims' rows."""
+    from get_b200 import synthetic
+    from get_b200.ddp import balance_claims
+    from get_b200.keywords import KeyWordSettings as K
+    from get_b200.step_graph import select_claims
+    rng = np.random.default_rng(3)
+    for world in (2, 4, 8):
+        cnt = rng.integers(1, 30, size=32 * world)
+        parts = balance_claims(cnt, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(cnt)))
+        loads = [int(cnt[p].sum()) for p in parts]
+        assert max(loads) - min(loads) <= 2, loads
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 6
+    w = synthetic.get_workload("tiny", batch_claims=9)
+    b = synthetic.make_batch(w, seed=5)
+    parts = balance_claims(b[K.EvidenceCountPerQuery], 2)
+    subs = [select_claims(b, p) for p in parts]
+    assert sum(s["pairs"] for s in subs) == b["pairs"]
+    off = np.concatenate([[0], np.cumsum(b[K.EvidenceCountPerQuery])])
+    for p, s in zip(parts, subs):
+        assert np.array_equal(s["labels"], b["labels"][p])
+        rows = np.concatenate([np.arange(off[c], off[c + 1]) for c in p])
+        assert np.array_equal(s[K.Evd_Docs_Adj], b[K.Evd_Docs_Adj][rows])
+        assert np.array_equal(s[K.EvidenceCountPerQuery], np.asarray(b[K.EvidenceCountPerQuery])[p])

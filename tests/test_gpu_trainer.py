@@ -154,9 +154,12 @@ def _ddp_worker(rank, world, port, q):
         ops.cross_entropy(m(q_, d_, **kw_), l_).backward()
         ref = {n: p.grad.detach().cpu().clone() for n, p in named}
         err = max(float((got[n] - ref[n]).abs().max()) for n in ref)
+        print("2-GPU vs 1-GPU gradient max abs diff: %.3e" % err, flush=True)
         q.put(err)
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    # captured graphs hold NCCL kernels: tearing the communicator down under them can block; leave like bench.py does
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
@@ -170,8 +173,8 @@ def test_two_gpu_gradients_equal_single_gpu_gradients():
     procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    err = q.get(timeout=600)
+    err = q.get(timeout=300)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-6, err
