@@ -156,6 +156,8 @@ def _ddp_worker(rank, world, port, q):
         err = max(float((got[n] - ref[n]).abs().max()) for n in ref)
         print("2-GPU vs 1-GPU gradient max abs diff: %.3e" % err, flush=True)
         q.put(err)
+        q.close()
+        q.join_thread()           # the result is flushed to the parent before this process leaves through os._exit
     dist.barrier()
     torch.cuda.synchronize()
     # captured graphs hold NCCL kernels: tearing the communicator down under them can block; leave like bench.py does
