@@ -88,8 +88,6 @@ SIGNATURES = {
     "get_gsl_fused_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P]),
     "get_graph_aggregate_bp": (_I, [_P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
     "get_gsl_fused_bp": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
-    "get_gsl_fused_sp": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _F, _U, _P, _P, _P, _P, _L, _L, _I, _P]),
-    "get_graph_split_slices": (_I, [_I, _I]),
     "get_neighbor_lists_rowptr_pitch": (_I, [_I]),
     "get_neighbor_lists_entry_capacity": (_I, [_I]),
     "get_build_neighbor_lists": (_I, [_P, _I, _I, _P, _P, _P, _P]),

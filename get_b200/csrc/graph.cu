@@ -1,4 +1,6 @@
-// Per-graph kernels of the GET hot path (HBM-bound part).
+// Per-graph kernels of the GET hot path on the DENSE adjacency: the op-level entry points (get_graph_aggregate_f32 / _bp,
+// get_gsl_fused_f32 / _bp, get_gsl_mask_adj_f32) and the fallback of the model for shapes the neighbour-list kernels do not
+// cover (N > 232, feature widths that are not multiples of 4). The model's default graph path is graph_lists.cu.
 //
 //  * <FUSED=false>: out[g] (+)= op(adj'[g]) @ x[g]                                   reference Models/BiDAF/wrapper.py:192
 //  * <FUSED=true> : node scorer (GGNN with out_features=1, wrapper.py:167) -> top-k keep set
@@ -516,291 +518,6 @@ __global__ void __launch_bounds__(GS_THREADS, 1) graph_smem_kernel(const __grid_
   }
 }
 
-// =====================================================================================================
-// Column-split path (the default fast path): one graph = `nsplit` INDEPENDENT 512-thread CTAs, each owning a slice of the
-// feature columns (aggregation is independent per column once the kept-node set is known). A slice of a Snopes graph is
-// 61 KB of features + the 40 KB adjacency, so TWO CTAs are co-resident per SM: one CTA's TMA loads and row stores overlap
-// the other's compute, and a 216-graph launch becomes 432 work items instead of two partial waves of whole graphs.
-// What makes the slices independent is that the scorer's projection s_p = dropout_s(F) . w_p (the only quantity that needs
-// whole feature rows) arrives precomputed: it is a by-product of the epilogue of the GEMM that wrote F (get_gemm_bp,
-// rowdot_out), or of a small row-dot kernel for the stand-alone entry points. Every CTA recomputes the cheap per-graph
-// part (neighbour lists, SpMV of the scorer, scalar GRU gates, top-k) from the adjacency it has to load anyway.
-//   * adjacency: one bulk copy; features: ONE 2-D TMA box {slice columns, N rows} (tensor map over (G*N, H));
-//   * neighbour lists built in place over the dense tile (rows with more than N/2 neighbours stay dense);
-//   * aggregation: half a warp per output row (a 38-quad slice keeps 38 of 48 lane slots busy), 128-bit shared loads,
-//     results leave as fp32 rows and / or bf16 planes for the next tensor-core contraction.
-// =====================================================================================================
-constexpr int GP_THREADS = 512;
-constexpr int GP_WARPS = GP_THREADS / 32;
-constexpr int GP_ROWS_PER_WARP = GS_MAX_N / GP_WARPS;   // 8
-constexpr size_t GP_SMEM_PER_CTA = 112 * 1024;          // two CTAs per SM
-
-struct SplitParams {
-  GraphParams g;
-  const float* sp_parts;   // (n_sp, G*N) partial scorer projections, summed in order
-  int n_sp;
-  int nsplit, qs;          // column slices per graph; float4 quads per slice
-};
-
-__device__ __forceinline__ void gp_tma_load_2d(void* dst, const void* map, int x, int y, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(gs_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(gs_smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
-
-struct alignas(64) TmapBytes { unsigned char b[128]; };
-
-// smem: [F slice N*WP f32 (row pitch WP = qs*4)] [adj N*N f32 -> per-row lists in place, N/2 entries of 8 B per row]
-//       [sp N] [score N] [cnt N i32] [rank N i32] [keep N u8] [mbarriers 2]
-template <bool FUSED, int NQH>
-__global__ void __launch_bounds__(GP_THREADS, 2) graph_split_kernel(const __grid_constant__ SplitParams sp, const __grid_constant__ TmapBytes fmap) {
-  extern __shared__ __align__(128) float smem[];
-  const GraphParams& p = sp.g;
-  const int g = blockIdx.x / sp.nsplit, slice = blockIdx.x - g * sp.nsplit;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = p.N, H = p.H, HQ = H >> 2;
-  const int q0 = slice * sp.qs;                        // first global quad of this CTA
-  const int WQ = min(sp.qs, HQ - q0);                  // quads owned
-  const int WP = sp.qs * 4;                            // smem row pitch in floats
-  const uint32_t salt = (FUSED && p.thr) ? __ldg(p.salt) : 0u;
-  const uint32_t seed_2 = p.seed_2 + salt;
-
-  float* sF = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~(uintptr_t)127);   // TMA destination: 128-byte aligned
-  float* sA = sF + (size_t)N * WP;
-  float* s_sp = sA + (size_t)N * N;
-  float* s_score = s_sp + N;
-  int* s_cnt = reinterpret_cast<int*>(s_score + N);
-  int* s_rank = s_cnt + N;
-  uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_rank + N);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_keep + ((N + 15) & ~15));   // [0] adjacency, [1] features
-
-#ifdef GETB_GRAPH_TIMELINE
-  __shared__ long long tl[10];
-  const long long t0 = clock64();
-#define GP_T(i) do { if (tid == 0) tl[i] = clock64() - t0; } while (0)
-#else
-#define GP_T(i) do { } while (0)
-#endif
-  const float* __restrict__ gadj = p.adj + (int64_t)g * N * N;
-  if (tid == 0) {
-    gs_mbar_init(&bars[0], 1);
-    gs_mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t abytes = (uint32_t)N * (uint32_t)N * 4u;
-    gs_mbar_expect_tx(&bars[0], abytes);
-    gs_bulk_g2s(sA, gadj, abytes, &bars[0]);
-    gs_mbar_expect_tx(&bars[1], (uint32_t)N * (uint32_t)WP * 4u);
-    gp_tma_load_2d(sF, &fmap, q0 * 4, g * N, &bars[1]);
-  }
-  if (tid < N) {
-    s_rank[tid] = 0;
-    if (!FUSED) s_keep[tid] = p.keep_in ? p.keep_in[(int64_t)g * N + tid] : (uint8_t)1;
-    if (FUSED) {
-      float v = 0.f;
-      for (int q = 0; q < sp.n_sp; ++q) v += __ldg(sp.sp_parts + (int64_t)q * p.G * N + (int64_t)g * N + tid);   // fixed order
-      s_sp[tid] = v;
-    }
-  }
-
-  // ---- neighbour lists in place: row i -> {byte offset of F row j, w_ij}; rows with more than N/2 neighbours stay dense
-  GP_T(0);
-  gs_mbar_wait(&bars[0], 0);
-  GP_T(1);
-  {
-    float wv[GP_ROWS_PER_WARP][4];
-#pragma unroll
-    for (int r = 0; r < GP_ROWS_PER_WARP; ++r) {
-      const int i = warp + r * GP_WARPS;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = c * 32 + lane;
-        wv[r][c] = (i < N && j < N) ? (p.transpose ? sA[(size_t)j * N + i] : sA[(size_t)i * N + j]) : 0.f;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < GP_ROWS_PER_WARP; ++r) {
-      const int i = warp + r * GP_WARPS;
-      if (i < N) {
-        unsigned nz[4];
-        int total = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          nz[c] = __ballot_sync(0xffffffffu, wv[r][c] != 0.f);
-          total += __popc(nz[c]);
-        }
-        if (total <= N / 2) {
-          float2* lr = reinterpret_cast<float2*>(sA + (size_t)i * N);
-          int pos = 0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (wv[r][c] != 0.f)
-              lr[pos + __popc(nz[c] & ((1u << lane) - 1u))] = make_float2(__int_as_float((c * 32 + lane) * WP * 4), wv[r][c]);
-            pos += __popc(nz[c]);
-          }
-          if (lane == 0) s_cnt[i] = total;
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {     // dense row of op(adj) (matters for transpose); aggregated by column scan
-            const int j = c * 32 + lane;
-            if (j < N) sA[(size_t)i * N + j] = wv[r][c];
-          }
-          if (lane == 0) s_cnt[i] = -1;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  GP_T(2);
-
-  const float inv_rowbytes = 1.0f / (float)(WP * 4);   // offsets are exact multiples of WP*4 < 2^24: rounding recovers j
-  if (FUSED) {
-    // ---- s_a = adj @ s_p + scalar GRU gates (GGNN with out_features = 1), one thread per node -------------------
-    if (tid < N) {
-      const int i = tid;
-      const int cnt = s_cnt[i];
-      float sa = 0.f;
-      if (cnt >= 0) {
-        const float2* lr = reinterpret_cast<const float2*>(sA + (size_t)i * N);
-        for (int e = 0; e < cnt; ++e) {
-          const float2 en = lr[e];
-          sa = fmaf(en.y, s_sp[__float2int_rn(__int2float_rn(__float_as_int(en.x)) * inv_rowbytes)], sa);
-        }
-      } else {
-        for (int j = 0; j < N; ++j) sa = fmaf(sA[(size_t)i * N + j], s_sp[j], sa);
-      }
-      const float wz0 = __ldg(p.gate + 0), bz0 = __ldg(p.gate + 1), wz1 = __ldg(p.gate + 2), bz1 = __ldg(p.gate + 3);
-      const float wr0 = __ldg(p.gate + 4), br0 = __ldg(p.gate + 5), wr1 = __ldg(p.gate + 6), br1 = __ldg(p.gate + 7);
-      const float wh0 = __ldg(p.gate + 8), bh0 = __ldg(p.gate + 9), wh1 = __ldg(p.gate + 10), bh1 = __ldg(p.gate + 11);
-      const float spv = s_sp[i];
-      const float z = sigmoidf_((wz0 * sa + bz0) + (wz1 * spv + bz1));
-      const float r = sigmoidf_((wr0 * sa + br0) + (wr1 * spv + br1));
-      const float h = tanhf((wh0 * sa + bh0) + (wh1 * (r * spv) + bh1));
-      const float sc = h * z + spv * (1.0f - z);
-      s_score[i] = sc;
-      if (p.score && slice == 0) p.score[(int64_t)g * N + i] = sc;
-    }
-    __syncthreads();
-    // ---- top-k by rank counting: thread (node i, slice of 32 candidates); ties -> lower index first -------------
-    {
-      const int i = tid & (GS_MAX_N - 1);
-      const int j0 = (tid >> 7) * 32;
-      if (i < N && j0 < N) {
-        const float si = s_score[i];
-        const int j1 = min(N, j0 + 32);
-        int rank = 0;
-        for (int j = j0; j < j1; ++j) {
-          const float sj = s_score[j];
-          rank += ((sj > si) || (sj == si && j < i)) ? 1 : 0;
-        }
-        if (rank) atomicAdd(&s_rank[i], rank);
-      }
-    }
-    __syncthreads();
-    if (tid < N) {
-      const uint8_t kp = s_rank[tid] < p.k;
-      s_keep[tid] = kp;
-      if (slice == 0) p.keep_out[(int64_t)g * N + tid] = kp;
-    }
-  }
-
-  // ---- features have landed: the layer-2 dropout draw is applied in place -----------------------------------------
-  GP_T(3);
-  gs_mbar_wait(&bars[1], 0);
-  GP_T(4);
-  if (FUSED && p.thr) {
-    for (int e = tid; e < N * WQ; e += GP_THREADS) {
-      const int i = e / WQ, q = e - i * WQ;
-      float4* f = reinterpret_cast<float4*>(sF + (size_t)i * WP) + q;
-      float4 v = *f;
-      drop_apply4(seed_2, ((uint64_t)g * N + i) * (uint64_t)H + (uint64_t)(q0 + q) * 4, p.thr, p.scale, v);
-      *f = v;
-    }
-  }
-  __syncthreads();
-  GP_T(5);
-
-  // ---- out[i, own columns] = sum_e w[i][e] * x[idx[i][e], own columns]; half a warp per row ------------------------
-  const bool masked = FUSED || (p.keep_in != nullptr);
-  const int hw = lane >> 4, hl = lane & 15;
-  const char* sFb = reinterpret_cast<const char*>(sF) + hl * 16;
-  const bool last_slice = slice == sp.nsplit - 1;
-  const int npq = last_slice ? ((((H + (p.pad_one ? 1 : 0)) + 7) & ~7) - H) >> 2 : 0;     // padding quads of the plane rows
-  for (int i = warp * 2 + hw; i < N; i += 2 * GP_WARPS) {
-    float4 acc[NQH];
-#pragma unroll
-    for (int u = 0; u < NQH; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int cnt = s_cnt[i];
-    const bool dropped = masked && s_keep[i] == 0;   // a dropped node keeps only its edges to kept nodes (wrapper.py:221-225)
-    if (cnt >= 0) {
-      const float2* lr = reinterpret_cast<const float2*>(sA + (size_t)i * N);
-#pragma unroll 2
-      for (int e = 0; e < cnt; ++e) {
-        const float2 en = lr[e];
-        float wj = en.y;
-        const int off = __float_as_int(en.x);
-        if (dropped && !s_keep[__float2int_rn(__int2float_rn(off) * inv_rowbytes)]) wj = 0.f;
-        const float4* row = reinterpret_cast<const float4*>(sFb + off);
-#pragma unroll
-        for (int u = 0; u < NQH; ++u) {
-          if (hl + u * 16 < WQ) {
-            const float4 f = row[u * 16];
-            acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
-            acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
-          }
-        }
-      }
-    } else {
-      for (int j = 0; j < N; ++j) {               // dense row (more than N/2 neighbours)
-        const float wj = sA[(size_t)i * N + j];
-        if (wj == 0.f || (dropped && !s_keep[j])) continue;
-        const float4* row = reinterpret_cast<const float4*>(sFb + (size_t)j * WP * 4);
-#pragma unroll
-        for (int u = 0; u < NQH; ++u) {
-          if (hl + u * 16 < WQ) {
-            const float4 f = row[u * 16];
-            acc[u].x = fmaf(wj, f.x, acc[u].x); acc[u].y = fmaf(wj, f.y, acc[u].y);
-            acc[u].z = fmaf(wj, f.z, acc[u].z); acc[u].w = fmaf(wj, f.w, acc[u].w);
-          }
-        }
-      }
-    }
-    float* orow = p.out ? p.out + ((int64_t)g * N + i) * H + (int64_t)q0 * 4 : nullptr;
-    __nv_bfloat16* prow = p.out_p ? p.out_p + ((int64_t)g * N + i) * p.ld_p + (int64_t)q0 * 4 : nullptr;
-#pragma unroll
-    for (int u = 0; u < NQH; ++u) {
-      const int q = hl + u * 16;
-      if (q < WQ) {
-        float4 v = acc[u];
-        if (p.accumulate) {
-          const float4 o = *(reinterpret_cast<const float4*>(orow) + q);
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-        if (orow) *(reinterpret_cast<float4*>(orow) + q) = v;
-        if (prow) {
-          const float vv[4] = {v.x, v.y, v.z, v.w};
-          planes_store4(prow + q * 4, p.ps_p, p.np_p, vv);
-        }
-      }
-    }
-    if (prow && hl < npq) {     // padding quads up to a multiple of 8 columns (room for the ones column when pad_one)
-      const float vv[4] = {(p.pad_one && hl == 0) ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
-      planes_store4(p.out_p + ((int64_t)g * N + i) * p.ld_p + H + hl * 4, p.ps_p, p.np_p, vv);
-    }
-  }
-#ifdef GETB_GRAPH_TIMELINE
-  __syncthreads();
-  GP_T(6);
-  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 150 || blockIdx.x == 400))
-    printf("GPDBG cta %d: init %lld adj_landed %lld lists %lld scores %lld F_landed %lld dropout %lld aggregate+store %lld\n", blockIdx.x,
-           tl[0], tl[1], tl[2], tl[3], tl[4], tl[5], tl[6]);
-#endif
-}
-
 // s_p[m] = dropout_s(F[m,:]) . wp  -- the scorer projection for the stand-alone entry points (in the model it is a by-product
 // of the epilogue of the GEMM that writes F); one warp per row
 __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ F, const float* __restrict__ wp, int64_t M, int H,
@@ -819,31 +536,6 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ F
   }
   acc = warp_sum(acc);
   if (lane == 0) out[m] = acc;
-}
-
-typedef void (*GraphSplitFn)(const SplitParams, const TmapBytes);
-static GraphSplitFn graph_split_fn(bool fused, int nqh) {
-  switch (nqh) {
-    case 1: return fused ? graph_split_kernel<true, 1> : graph_split_kernel<false, 1>;
-    case 2: return fused ? graph_split_kernel<true, 2> : graph_split_kernel<false, 2>;
-    case 3: return fused ? graph_split_kernel<true, 3> : graph_split_kernel<false, 3>;
-    default: return fused ? graph_split_kernel<true, 4> : graph_split_kernel<false, 4>;
-  }
-}
-
-// plan of the column-split path: smallest number of slices whose CTA fits twice per SM; 0 = not applicable
-static int graph_split_plan(const GraphParams& p, bool fused, int& qs, size_t& smem) {
-  if ((p.H % 4) != 0 || (p.N % 2) != 0 || p.N > GS_MAX_N || !aligned16(p.adj) || !aligned16(p.x) || (p.out && !aligned16(p.out)))
-    return 0;
-  const int hq = p.H / 4;
-  for (int s = 1; s <= 8; ++s) {
-    qs = (hq + s - 1) / s;
-    if (qs > 64 || (s - 1) * qs >= hq) continue;
-    smem = ((size_t)p.N * qs * 4 + (size_t)p.N * p.N + 4 * (size_t)p.N) * sizeof(float) + (((size_t)p.N + 15) & ~(size_t)15) +
-           2 * sizeof(uint64_t) + 128;
-    if (smem <= GP_SMEM_PER_CTA) return s;
-  }
-  return 0;
 }
 
 typedef void (*GraphSmemFn)(const GraphParams);
@@ -885,8 +577,7 @@ __global__ void __launch_bounds__(GRAPH_THREADS) gsl_mask_adj_kernel(const float
   }
 }
 
-static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char* name, const float* sp_parts = nullptr,
-                        int n_sp = 0) {
+static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char* name) {
   GETB_REQUIRE(p.G >= 0 && p.N > 0 && p.H > 0, "%s: bad sizes G=%d N=%d H=%d", name, p.G, p.N, p.H);
   GETB_REQUIRE(p.H <= 32 * 4 * MAX_QUADS_PER_LANE, "%s: H=%d exceeds %d", name, p.H, 32 * 4 * MAX_QUADS_PER_LANE);
   GETB_REQUIRE(p.out || p.out_p, "%s: no output", name);
@@ -896,47 +587,6 @@ static int launch_graph(GraphParams& p, bool fused, cudaStream_t st, const char*
                      (p.ld_p % 4) == 0 && (p.ps_p % 4) == 0 && p.np_p >= 1 && p.np_p <= 3 && p.ld_p >= ((p.H + (p.pad_one ? 1 : 0) + 7) & ~7),
                  "%s: plane output needs H %% 4 == 0 and aligned tensors", name);
   if (p.G == 0) return 0;
-  {
-    // column-split path: `nsplit` independent CTAs per graph, two co-resident per SM. The fused kernel needs the scorer
-    // projection precomputed (sp_parts); the plain aggregation needs nothing extra.
-    static int use_split = -1;
-    if (use_split < 0) {
-      const char* e = getenv("GET_B200_GRAPH_SPLIT");
-      use_split = e ? atoi(e) : 0;   // measured slower than one CTA per graph on B200 (issue-bound phases are duplicated per slice)
-    }
-    int qs = 0;
-    size_t smem = 0;
-    const int S = (use_split && (!fused || sp_parts) && (int64_t)p.G * 8 < (int64_t)1 << 30) ? graph_split_plan(p, fused, qs, smem) : 0;
-    if (S > 0) {
-      SplitParams spp;
-      spp.g = p; spp.sp_parts = sp_parts; spp.n_sp = n_sp; spp.nsplit = S; spp.qs = qs;
-      TmapBytes fmap;
-      if (!make_tensor_map(&fmap, p.x, 1, 2, p.H, (int64_t)p.G * p.N, 1, p.H, 0, qs * 4, p.N, 1, 0)) return -3;
-      const int nqh = (qs + 15) / 16;
-      GraphSplitFn fn = graph_split_fn(fused, nqh);
-      static bool attr_s[2][5] = {};
-      if (!attr_s[fused ? 1 : 0][nqh]) {
-        // two CTAs per SM need the full shared-memory carve-out (the default carve-out only guarantees ONE resident CTA)
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_PER_CTA) != cudaSuccess ||
-            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
-          set_error("%s: cannot opt in to %d bytes of shared memory", name, (int)GP_SMEM_PER_CTA);
-          (void)cudaGetLastError();
-          return -2;
-        }
-        if (getenv("GET_B200_GRAPH_DEBUG")) {
-          int nb = 0;
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, GP_THREADS, smem);
-          fprintf(stderr, "graph_split_kernel<%d,%d>: %d slices, %zu B smem, %d CTAs/SM\n", (int)fused, nqh, S, smem, nb);
-        }
-        attr_s[fused ? 1 : 0][nqh] = true;
-      }
-      fn<<<p.G * S, GP_THREADS, smem, st>>>(spp, fmap);
-      GETB_CHECK_LAUNCH(name);
-      return 0;
-    }
-    GETB_REQUIRE(!(fused && sp_parts), "%s: precomputed scorer projections need the column-split path (N <= %d, N %% 2 == 0, H %% 4 == 0)",
-                 name, GS_MAX_N);
-  }
   {
     // single-CTA path: the whole graph (features + adjacency) staged in shared memory by TMA bulk copies
     const size_t need = ((size_t)p.N * p.H + 2 * (size_t)p.N * p.N + 4 * (size_t)p.N) * sizeof(float) +
@@ -1043,34 +693,6 @@ extern "C" int get_gsl_fused_bp(const float* adj, const float* F, const float* w
   p.seed_s = seed_scorer; p.seed_2 = seed_layer2; p.salt = dropout_salt_ptr();
   p.score = score; p.keep_out = keep;
   return launch_graph(p, true, (cudaStream_t)stream, "get_gsl_fused_bp");
-}
-
-extern "C" int get_gsl_fused_sp(const float* adj, const float* F, const float* sp_parts, int n_sp, const float* gate, int G, int N,
-                                int H, int k, float drop_p, uint32_t seed_layer2, float* score, uint8_t* keep, float* out,
-                                void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream) {
-  GETB_REQUIRE(adj && F && sp_parts && n_sp >= 1 && gate && keep && (out || planes), "get_gsl_fused_sp: null pointer");
-  GETB_REQUIRE(k >= 0 && k <= N, "get_gsl_fused_sp: k=%d out of [0,%d]", k, N);
-  GETB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "get_gsl_fused_sp: dropout probability must be in [0,1)");
-  GraphParams p;
-  memset(&p, 0, sizeof(p));
-  p.adj = adj; p.x = F; p.out = out; p.G = G; p.N = N; p.H = H;
-  p.out_p = reinterpret_cast<__nv_bfloat16*>(planes); p.ld_p = ld_p; p.ps_p = plane_stride; p.np_p = nplanes;
-  p.gate = gate; p.k = k;
-  p.thr = drop_p > 0.f ? drop_threshold(drop_p) : 0;
-  p.scale = 1.0f / (1.0f - drop_p);
-  p.seed_2 = seed_layer2; p.salt = dropout_salt_ptr();
-  p.score = score; p.keep_out = keep;
-  return launch_graph(p, true, (cudaStream_t)stream, "get_gsl_fused_sp", sp_parts, n_sp);
-}
-
-extern "C" int get_graph_split_slices(int N, int H) {
-  GraphParams p;
-  memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H;
-  p.adj = reinterpret_cast<const float*>(16); p.x = reinterpret_cast<const float*>(16);
-  int qs = 0;
-  size_t smem = 0;
-  return graph_split_plan(p, true, qs, smem);
 }
 
 extern "C" int get_rowdot_f32(const float* F, const float* w, int64_t M, int H, float drop_p, uint32_t seed, float* out,

@@ -533,8 +533,6 @@ def gsl_fused(adj, feat, wp, gate, k, drop_p=0.0, seed_scorer=0, seed_layer2=0, 
     out = alloc_planes(planes_n, G * N, H, feat.device) if planes_n else torch.empty_like(feat)
     adj = as_lists(adj)
     mode = "lists" if adj.usable(H) else "dense"
-    if mode == "dense" and int(lib.get_graph_split_slices(N, H)) > 0 and os.environ.get("GET_B200_GRAPH_SPLIT", "0") != "0":
-        mode = "split"
     if mode != "dense" and sp_parts is None:
         sp_parts = rowdot(feat.view(G * N, H), wp, drop_p, seed_scorer)
     if mode == "dense":
@@ -567,11 +565,7 @@ def _gsl_launch(adj, feat, wp, gate, k, drop_p, s1, s2, score, keep, out, sp_par
                    "get_gsl_gather")
         return
     adj = dense_adj(adj)
-    if mode == "split":
-        assert sp_parts.is_contiguous() and sp_parts.shape[1] == G * N
-        _lib.check(lib.get_gsl_fused_sp(adj.data_ptr(), feat.data_ptr(), sp_parts.data_ptr(), sp_parts.shape[0], gate.data_ptr(), G, N,
-                                        H, k, drop_p, s2, _ptr(score), keep.data_ptr(), *plane_args, _stream()), "get_gsl_fused_sp")
-    elif pl is not None:
+    if pl is not None:
         _lib.check(lib.get_gsl_fused_bp(adj.data_ptr(), feat.data_ptr(), wp.data_ptr(), gate.data_ptr(), G, N, H, k, drop_p, s1, s2,
                                         _ptr(score), keep.data_ptr(), None, pl.ptr, pl.ld, pl.plane_stride, pl.nplanes,
                                         _stream()), "get_gsl_fused_bp")

@@ -250,17 +250,6 @@ int get_gsl_fused_bp(const float* adj, const float* F, const float* wp, const fl
                      float drop_p, uint32_t seed_scorer, uint32_t seed_layer2, float* score, uint8_t* keep,
                      float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
 
-/* The fused GSL kernel with the scorer projection s_p = dropout_s(F) . w_p PRECOMPUTED (n_sp partial vectors of G*N floats,
- * summed in order): a by-product of the epilogue of the contraction that wrote F (get_gemm_bp, rowdot_out), or of
- * get_rowdot_f32. Without the need for whole feature rows every graph is processed by several independent CTAs that own
- * column slices of F (two co-resident per SM: loads and stores of one overlap the compute of the other). Same outputs as
- * get_gsl_fused_bp; drop_p / seed_layer2 = the nn.Dropout draw of feat_prop2 (the scorer's draw went into s_p). */
-int get_gsl_fused_sp(const float* adj, const float* F, const float* sp_parts, int n_sp, const float* gate, int G, int N,
-                     int H, int k, float drop_p, uint32_t seed_layer2, float* score, uint8_t* keep, float* out,
-                     void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
-/* Column slices per graph the split kernels use for (N, H); 0 = shape not covered (N > 128, odd N, H % 4 != 0, ...): then
- * get_gsl_fused_f32 / _bp (one CTA per graph, or the generic kernel) are the entry points. */
-int get_graph_split_slices(int N, int H);
 /* out[m] = dropout(F[m,:]; drop_p, seed, index m*H + c) . w   (the `proj` of GGNN(H -> 1), wrapper.py:191). */
 int get_rowdot_f32(const float* F, const float* w, int64_t M, int H, float drop_p, uint32_t seed, float* out, void* stream);
 
@@ -285,7 +274,10 @@ int get_build_neighbor_lists(const float* adj, int G, int N, void* ent, int32_t*
 int get_graph_gather(const void* ent, const int32_t* rowptr, const int32_t* used, const float* x, const uint8_t* keep,
                      float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, int pad_one, int G, int N,
                      int H, int accumulate, void* stream);
-/* The fused GSL kernel on lists (same outputs and argument meaning as get_gsl_fused_sp). */
+/* The fused GSL kernel on lists: same outputs as get_gsl_fused_bp, with the scorer projection s_p = dropout_s(F) . w_p
+ * PRECOMPUTED (n_sp partial vectors of G*N floats, summed in order): a by-product of the epilogue of the contraction that
+ * wrote F (get_gemm_bp, rowdot_out), or of get_rowdot_f32. drop_p / seed_layer2 = the nn.Dropout draw of feat_prop2 (the
+ * scorer's draw went into s_p). */
 int get_gsl_gather(const void* ent, const int32_t* rowptr, const int32_t* used, const float* F, const float* sp_parts, int n_sp,
                    const float* gate, int G, int N, int H, int k, float drop_p, uint32_t seed_layer2, float* score,
                    uint8_t* keep, float* out, void* planes, int64_t ld_p, int64_t plane_stride, int nplanes, void* stream);
