@@ -568,17 +568,38 @@ struct BpDstList {
 
 __global__ void __launch_bounds__(256) bp_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int64_t ws_ld,
                                                                const __grid_constant__ BpDstList L, int accumulate) {
-  // block (x over columns, y over destination blocks x row chunks)
+  // Fixed-order sum over the split-K partials (deterministic), scattered into the destination blocks. A thread owns four
+  // consecutive columns of a row: 128-bit loads from the workspace (its pitch and the block's first column are multiples
+  // of 4 floats in every weight-gradient call; anything else takes the scalar path), all splits of a quad in flight.
+  const int64_t zs = (int64_t)M * ws_ld;
   for (int b = 0; b < L.n; ++b) {
     const get_bp_dst& d = L.d[b];
-    const int64_t total = (int64_t)d.nrows * d.ncols;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-      const int r = (int)(e / d.ncols), c = (int)(e % d.ncols);
-      const float* src = ws + (int64_t)(d.row0 + r) * ws_ld + (d.col0 + c);
-      float acc = 0.f;
-      for (int z = 0; z < splits; ++z) acc += src[(int64_t)z * M * ws_ld];
-      float* o = d.dst + (int64_t)r * d.ld + c;
-      *o = accumulate ? *o + acc : acc;
+    const bool vec = (d.col0 & 3) == 0 && (ws_ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(ws) & 15u) == 0);
+    const unsigned nq = vec ? (unsigned)((d.ncols + 3) >> 2) : (unsigned)d.ncols;
+    const unsigned total = (unsigned)d.nrows * nq;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const unsigned r = e / nq, q = e - r * nq;
+      if (vec) {
+        const int c = (int)q * 4;
+        const float* src = ws + (int64_t)(d.row0 + r) * ws_ld + (d.col0 + c);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int z = 0; z < splits; ++z) {
+          const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)z * zs);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float* o = d.dst + (int64_t)r * d.ld + c;
+        const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c + u < d.ncols) o[u] = accumulate ? o[u] + a4[u] : a4[u];
+      } else {
+        const float* src = ws + (int64_t)(d.row0 + r) * ws_ld + (d.col0 + (int)q);
+        float acc = 0.f;
+        for (int z = 0; z < splits; ++z) acc += src[(int64_t)z * zs];
+        float* o = d.dst + (int64_t)r * d.ld + q;
+        *o = accumulate ? *o + acc : acc;
+      }
     }
   }
 }
@@ -1029,18 +1050,18 @@ extern "C" int get_bp_splitk_reduce(const float* workspace, int splits, int M, i
   GETB_REQUIRE(workspace && dsts && ndst >= 1 && ndst <= GET_BP_MAX_DST && splits >= 1, "get_bp_splitk_reduce: bad arguments");
   BpDstList L;
   memset(&L, 0, sizeof(L));
-  int64_t total = 0;
+  int64_t total = 0, maxq = 0;
   for (int b = 0; b < ndst; ++b) {
     const get_bp_dst& d = dsts[b];
     GETB_REQUIRE(d.dst && d.nrows >= 0 && d.ncols >= 0 && d.row0 >= 0 && d.row0 + d.nrows <= M && d.col0 >= 0 && d.col0 + d.ncols <= ws_ld,
                  "get_bp_splitk_reduce: destination block %d out of range", b);
     L.d[b] = d;
     total += (int64_t)d.nrows * d.ncols;
+    maxq = std::max<int64_t>(maxq, (int64_t)d.nrows * ((d.ncols + 3) / 4));
   }
   L.n = ndst;
   if (total == 0) return 0;
-  int grid = ceil_div(total / ndst + 1, 256);
-  if (grid > 4 * BP_SMS) grid = 4 * BP_SMS;
+  int grid = (int)std::min<int64_t>(ceil_div(maxq, (int64_t)256), 4 * BP_SMS);   // every destination block is swept by the whole grid
   if (grid < 1) grid = 1;
   bp_splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(workspace, splits, M, ws_ld, L, accumulate);
   GETB_CHECK_LAUNCH("get_bp_splitk_reduce");

@@ -287,22 +287,68 @@ __global__ void __launch_bounds__(128) embedding_rows_fwd_kernel(const float* __
   if (v < 0) v = 0;
   for (int c = threadIdx.x; c < E; c += blockDim.x) out[(int64_t)r * ld_out + c] = __ldg(table + v * E + c);
 }
-__global__ void __launch_bounds__(128) embedding_rows_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const int64_t* __restrict__ idx,
-                                                                 int R, int E, float* __restrict__ dtable, int accumulate) {
-  // block = one table row; thread = one column; the looked-up rows are visited in index order (deterministic sum)
-  extern __shared__ int s_idx[];                      // the R looked-up ids (-1 -> 0)
-  const int v = blockIdx.x;
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+constexpr int EB_THREADS = 512, EB_GROUPS = 4, EB_COLS = EB_THREADS / EB_GROUPS;
+__global__ void __launch_bounds__(EB_THREADS) embedding_rows_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const int64_t* __restrict__ idx,
+                                                                        int R, int V, int E, float* __restrict__ dtable) {
+  // block = one looked-up row r0. Only the FIRST occurrence of a table id does work: it lists every occurrence of that id
+  // (index order), sums their gradient rows -- four thread groups own consecutive quarters of the list, eight independent
+  // loads in flight per thread, partial sums combined in a fixed order (deterministic) -- and adds the total to the table
+  // row once. The padding id (-1 -> row 0) occurs in most slots of a batch: its list is what sets the kernel's time.
+  extern __shared__ int s_idx[];                      // [R] looked-up ids (-1 -> 0), then [R] the occurrence list
+  __shared__ int s_dup, s_n;
+  __shared__ float s_part[EB_GROUPS][EB_COLS];
+  int* s_list = s_idx + R;
+  const int r0 = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_dup = 0;
+  for (int r = tid; r < R; r += EB_THREADS) {
     const int64_t id = idx[r];
     s_idx[r] = id < 0 ? 0 : (int)id;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+  const int v = s_idx[r0];
+  if (v >= V) __trap();                               // an id outside the table must fail loudly
+  bool dup = false;
+  for (int r = tid; r < r0; r += EB_THREADS) dup |= s_idx[r] == v;
+  if (dup) s_dup = 1;
+  __syncthreads();
+  if (s_dup) return;
+  if (tid < 32) {                                     // occurrence list in index order (one warp, ballot compaction)
+    int n = 0;
+    for (int base = r0; base < R; base += 32) {
+      const int r = base + lane;
+      const bool hit = r < R && s_idx[r] == v;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) s_list[n + __popc(m & ((1u << lane) - 1u))] = r;
+      n += __popc(m);
+    }
+    if (lane == 0) s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n, grp = tid / EB_COLS, col = tid - grp * EB_COLS;
+  const int per = (n + EB_GROUPS - 1) / EB_GROUPS, lo = min(n, grp * per), hi = min(n, lo + per);
+  for (int c0 = 0; c0 < E; c0 += EB_COLS) {
+    const int c = c0 + col;
     float acc = 0.f;
-    for (int r = 0; r < R; ++r)
-      if (s_idx[r] == v) acc += g[(int64_t)r * ld_g + c];
-    float* d = dtable + (int64_t)v * E + c;
-    *d = accumulate ? *d + acc : acc;
+    if (c < E) {
+      int k = lo;
+      for (; k + 8 <= hi; k += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = g[(int64_t)s_list[k + u] * ld_g + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += t[u];
+      }
+      for (; k < hi; ++k) acc += g[(int64_t)s_list[k] * ld_g + c];
+    }
+    s_part[grp][col] = acc;
+    __syncthreads();
+    if (grp == 0 && c < E) {
+      float tot = s_part[0][col];
+#pragma unroll
+      for (int q = 1; q < EB_GROUPS; ++q) tot += s_part[q][col];
+      dtable[(int64_t)v * E + c] += tot;
+    }
+    __syncthreads();
   }
 }
 
@@ -567,8 +613,8 @@ extern "C" int get_embedding_rows_fwd_f32(const float* table, int V, int E, cons
 extern "C" int get_embedding_rows_bwd_f32(const float* g, int64_t ld_g, const int64_t* idx, int R, int V, int E, float* dtable,
                                           int accumulate, void* stream) {
   GETB_REQUIRE(g && idx && dtable && V >= 1 && E >= 1 && R >= 0 && ld_g >= E, "get_embedding_rows_bwd_f32: bad arguments");
-  GETB_REQUIRE((size_t)R * sizeof(int) <= 160 * 1024, "get_embedding_rows_bwd_f32: at most 40960 looked-up rows per call");
-  const size_t smem = (size_t)(R > 0 ? R : 1) * sizeof(int);
+  GETB_REQUIRE((size_t)R * 2 * sizeof(int) <= 160 * 1024, "get_embedding_rows_bwd_f32: at most 20480 looked-up rows per call");
+  const size_t smem = (size_t)(R > 0 ? R : 1) * 2 * sizeof(int);
   if (smem > 48 * 1024) {
     static bool done = false;
     if (!done) {
@@ -576,7 +622,15 @@ extern "C" int get_embedding_rows_bwd_f32(const float* g, int64_t ld_g, const in
       done = true;
     }
   }
-  embedding_rows_bwd_kernel<<<V, 128, smem, (cudaStream_t)stream>>>(g, ld_g, idx, R, E, dtable, accumulate);
+  if (!accumulate) {
+    if (cudaMemsetAsync(dtable, 0, (size_t)V * E * sizeof(float), (cudaStream_t)stream) != cudaSuccess) {
+      (void)cudaGetLastError();
+      getb::set_error("get_embedding_rows_bwd_f32: memset failed");
+      return -2;
+    }
+  }
+  if (R == 0) return 0;
+  embedding_rows_bwd_kernel<<<R, EB_THREADS, smem, (cudaStream_t)stream>>>(g, ld_g, idx, R, V, E, dtable);
   GETB_CHECK_LAUNCH("get_embedding_rows_bwd_f32");
   return 0;
 }

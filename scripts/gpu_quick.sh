@@ -1,8 +1,7 @@
 #!/bin/bash
-# quick GPU check: parity tests + bench line
-TAG=${1:-q}
+# quick check after a kernel change: all GPU tests, then the short bench line
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -q --maxfail=20 --tb=short -p no:cacheprovider > $OUT/tests_$TAG.log 2>&1
-tail -12 $OUT/tests_$TAG.log | cut -c1-300
-timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 --tb=short -p no:cacheprovider > $OUT/tests_q.log 2>&1; grep -v "Warn\|warn" $OUT/tests_q.log | tail -12 | cut -c1-220
+timeout 400 python bench.py --quick --steps 30 --warmup 5 > $OUT/bench_quick.json 2> $OUT/bench_quick.err; python -c "
+import json; d=json.load(open('$OUT/bench_quick.json')); print('ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'roofline', {k: d['roofline'][k] for k in ('frac','avg_launch_ms','list_build_ms')})"; tail -2 $OUT/bench_quick.err | cut -c1-200

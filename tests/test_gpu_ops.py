@@ -379,3 +379,27 @@ def test_device_word_graphs_match_host_construction(T, N, window, vocab):
         assert np.array_equal(nodes[g].cpu().numpy(), rn)
         ref32 = torch.from_numpy(ra).float()
         assert torch.equal(adj[g].cpu(), ref32), "graph %d: max diff %g" % (g, float((adj[g].cpu() - ref32).abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,E,R", [(512, 128, 990), (7, 128, 33), (3605, 128, 1200), (5, 12, 1)])
+def test_embedding_rows_forward_backward_match_torch(V, E, R):
+    """Source-embedding lookup (base_model.py:184-188; id -1 reads row 0, gbss.py:166-168) and its dense table gradient:
+    duplicates summed in index order (deterministic), untouched rows exactly zero."""
+    from get_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(V + R)
+    table = torch.randn(V, E, device="cuda", generator=g).requires_grad_(True)
+    idx = torch.randint(-1, min(V, 40), (R,), device="cuda", generator=g)          # many duplicates, some -1
+    out = ops.embedding_rows(table, idx)
+    ref_table = table.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.embedding(idx.clamp(min=0), ref_table)
+    assert torch.equal(out, ref)
+    w = torch.randn(R, E, device="cuda", generator=g)
+    (out * w).sum().backward()
+    (ref * w).sum().backward()
+    assert (table.grad - ref_table.grad).abs().max().item() <= 1e-5 * max(1.0, ref_table.grad.abs().max().item())
+    assert (table.grad[40:] == 0).all()
+    g1 = table.grad.clone()
+    table.grad = None
+    (ops.embedding_rows(table, idx) * w).sum().backward()
+    assert torch.equal(table.grad, g1)                                             # deterministic
