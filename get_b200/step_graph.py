@@ -13,6 +13,7 @@ gradients are unchanged (every claim is independent of the others, SURVEY.md sec
 Dropout: a replay repeats the captured kernel arguments, so the per-step variation of the masks comes from the
 library's device salt word, advanced by the first node of the graph (include/get_b200.h, get_dropout_salt_advance).
 """
+import collections
 import os
 import copy
 from typing import Dict, Optional, Tuple
@@ -163,7 +164,7 @@ class CapturedTrainStep(object):
     the shape is new on this rank, so ranks stay in lock-step as long as they call step() equally often."""
 
     def __init__(self, model, optimizer=None, reducer=None, loss_fn=None, collective_in_graph: bool = True,
-                 accumulate: bool = False):
+                 accumulate: bool = False, max_graphs: int = 32):
         """accumulate=True (micro-batching, needs an attached reducer): the captured step is [forward, loss * loss_scale,
         backward] only -- gradients accumulate in the reducer's bucket across calls; the caller zeroes the bucket, runs the
         all-reduce and the optimizer once per optimizer step."""
@@ -177,7 +178,11 @@ class CapturedTrainStep(object):
             collective_in_graph = False
         self.split_tail = (not collective_in_graph) and reducer is not None and reducer.world > 1
         self.loss_fn = loss_fn or ops.cross_entropy
-        self.slots: Dict[Tuple, _Slot] = {}
+        # one graph (with its private pool of activations, ~4 MB per claim-evidence pair) per padded batch shape: the cache is
+        # bounded, least-recently-used shapes are dropped and re-captured on demand (real Snopes batches span 32..960 pairs)
+        self.slots: "collections.OrderedDict[Tuple, _Slot]" = collections.OrderedDict()
+        self.max_graphs = max(1, int(max_graphs))
+        self.evictions = 0
         self.device = next(model.parameters()).device
         if reducer is not None:
             reducer.init_collective()    # communicator created here, never inside a capture
@@ -331,10 +336,16 @@ class CapturedTrainStep(object):
         key = self._key(query, document, kw, n_real, global_claims)
         s = self.slots.get(key)
         if s is None:
+            while len(self.slots) >= self.max_graphs:
+                torch.cuda.synchronize()            # nothing in flight may still replay the graph that is dropped
+                _, old = self.slots.popitem(last=False)
+                del old
+                self.evictions += 1
             s = self._build(query, document, labels, kw, n_real, global_claims)
             self.slots[key] = s
             # the capture itself executes nothing: fall through and replay once so that this call IS a step
         else:
+            self.slots.move_to_end(key)
             self._copy_in(s, query, document, labels, kw)
         s.graph.replay()
         self.replayed_launches += s.launches

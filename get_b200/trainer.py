@@ -56,7 +56,8 @@ def classification_metrics(labels: Sequence[int], preds: Sequence[int], probs: S
 
 class GETTrainer(object):
     def __init__(self, model, lr: float = 1e-4, reg_l2: float = 1e-3, n_iter: int = 100, early_stopping_patience: int = 10,
-                 saved_model: Optional[str] = None, pad_pairs_to: int = 64, flat_adam: bool = True, log: Callable = None):
+                 saved_model: Optional[str] = None, pad_pairs_to: int = 64, flat_adam: bool = True, log: Callable = None,
+                 max_graphs: int = 32):
         self.model = model
         self.device = next(model.parameters()).device
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -67,7 +68,8 @@ class GETTrainer(object):
             self.optimizer = FlatAdam(self.reducer, lr=lr, weight_decay=reg_l2)            # declare_fitter.py:57-61
         else:
             self.optimizer = torch.optim.Adam([p for _, p in named], lr=lr, weight_decay=reg_l2, fused=True, capturable=True)
-        self.stepper = CapturedTrainStep(model, self.optimizer, self.reducer)
+        # batches are padded to multiples of `pad_pairs_to` pairs, so real Snopes batches (32..960 pairs) need at most 15 shapes
+        self.stepper = CapturedTrainStep(model, self.optimizer, self.reducer, max_graphs=max_graphs)
         self.n_iter, self.patience, self.saved_model = int(n_iter), early_stopping_patience, saved_model
         self.pad_pairs_to = int(pad_pairs_to)
         self.log = log or (lambda *a: None)

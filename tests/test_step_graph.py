@@ -132,6 +132,39 @@ def test_captured_step_with_optimizer_trains_like_eager():
 
 
 @pytest.mark.gpu
+def test_bounded_graph_cache_evicts_and_recaptures():
+    """real Snopes batches span 32..960 pairs -> many padded shapes. The graph cache is bounded (LRU); a shape
+    that was dropped is re-captured on demand and the trajectory is the one of an unbounded cache."""
+    from get_b200.ddp import FlatAdam, FlatGradAllReduce, trainable_named_parameters
+    from get_b200.model import Graph_basedSemantiStructure
+    from get_b200.step_graph import CapturedTrainStep
+    dev = "cuda"
+    w = synthetic.get_workload("snopes", batch_claims=3, vocab=300, n_article_sources=8)
+    batches = [pad_batch(synthetic.make_batch(w, seed=s), 16) for s in range(1, 7)]
+    shapes = {b[K.DocContentNoPaddingEvidence].shape[0] for b in batches}
+    assert len(shapes) >= 3, shapes
+    tens = [synthetic.batch_to_torch(b, device=dev) for b in batches]
+    order = [0, 1, 2, 3, 4, 5, 0, 1, 2, 0]
+
+    def run(max_graphs):
+        torch.manual_seed(4)
+        m = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=True)).to(dev).eval()
+        named = trainable_named_parameters(m)
+        red = FlatGradAllReduce([p for _, p in named], names=[n for n, _ in named])
+        opt = FlatAdam(red, lr=1e-3, weight_decay=1e-3)
+        st = CapturedTrainStep(m, opt, red, max_graphs=max_graphs)
+        losses = [float(st.step(*tens[i], batches[i]["n_real_claims"])) for i in order]
+        red.detach()
+        return losses, st.n_graphs(), st.evictions
+
+    la, na, ea = run(32)
+    lb, nb, eb = run(2)
+    assert ea == 0 and na == len({(b["query"].shape[0], b[K.DocContentNoPaddingEvidence].shape[0], b["n_real_claims"]) for b in batches})
+    assert nb <= 2 and eb >= 3
+    assert np.allclose(la, lb, rtol=0, atol=1e-6), (la, lb)
+
+
+@pytest.mark.gpu
 def test_prefetched_inputs_give_the_same_step():
     from get_b200.model import Graph_basedSemantiStructure
     from get_b200.step_graph import CapturedTrainStep
