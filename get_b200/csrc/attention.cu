@@ -14,7 +14,7 @@
 
 namespace getb {
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 512;   // 220 groups on 148 SMs: the kernels are latency chains per warp, so more warps per group
 constexpr int ATT_WARPS = ATT_THREADS / 32;
 constexpr int ATT_MAX_HEADS = 8;
 
@@ -370,7 +370,7 @@ extern "C" int get_att_pool_fwd_f32(const float* t, const float* right, int64_t 
   p.t = t; p.right = right; p.ld_right = ld_right; p.W2 = W2; p.mask = mask;
   p.G = G; p.P = P; p.H = H; p.Dr = Dr; p.C = C; p.att = att; p.pooled = pooled; p.ld_pooled = ld_pooled;
   p.vec = (H % 4) == 0 && (Dr % 4) == 0 && (ld_right % 4) == 0 && aligned16(t) && aligned16(right);
-  int dchunk = (3072 / C) / 128 * 128;      // <= 96 KB of partial sums
+  int dchunk = (24576 / ATT_WARPS / C) / 128 * 128;      // <= 96 KB of partial sums
   if (dchunk < 128) dchunk = 128;
   if (dchunk > Dr) dchunk = Dr;
   p.dchunk = dchunk;

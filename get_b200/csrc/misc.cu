@@ -20,14 +20,22 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 const uint32_t* dropout_salt_ptr() {
-  static uint32_t* salt = nullptr;   // one word per process (one process per GPU); allocated on first use, never freed
-  static std::once_flag once;
-  std::call_once(once, [] {
+  // one word per DEVICE (normally one process per GPU, but the device current at library-load time need not be the one the
+  // process computes on); allocated on first use on that device, never freed
+  static uint32_t* salt[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (!salt[dev]) {
     uint32_t* ptr = nullptr;
-    if (cudaMalloc(&ptr, 256) == cudaSuccess && cudaMemset(ptr, 0, 256) == cudaSuccess) salt = ptr;
+    if (cudaMalloc(&ptr, 256) == cudaSuccess && cudaMemset(ptr, 0, 256) == cudaSuccess) salt[dev] = ptr;
     else (void)cudaGetLastError();
-  });
-  return salt;
+  }
+  return salt[dev];
 }
 
 // ---- GGNN backward, element-wise stage (reference forward Models/BiDAF/wrapper.py:194-206)
