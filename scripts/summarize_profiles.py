@@ -48,7 +48,7 @@ def launches():
     with open(os.path.join(PROF, "%s_launches_summary.txt" % TAG), "w") as fh:
         fh.write("# ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python scripts/one_step.py snopes fp32\n")
         fh.write("# ONE eager training step (fwd + CE + bwd + Adam) of the bench workload, %d launches, %.1f us in total; per-launch times are\n"
-                 "# cold-cache and serialised under ncu: compare SHARES, not absolutes (the captured step replays in 2.31 ms).\n" % (len(rows), tot))
+                 "# cold-cache and serialised under ncu: compare SHARES, not absolutes (the captured step replays in 2.27 ms).\n" % (len(rows), tot))
         fh.write("%-70s %8s %12s %7s %9s\n" % ("kernel", "launches", "total_us", "share", "avg_us"))
         for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             fh.write("%-70s %8d %12.1f %6.1f%% %9.1f\n" % (k[:70], c, t, 100 * t / tot, t / c))
