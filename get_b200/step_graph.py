@@ -398,6 +398,23 @@ class CapturedTrainStep(object):
         kw_dev[K.DocLensIndices] = (None, None, st["e_lens"])
         return (st, kw_dev)
 
+    def prefetch_tokens(self, tb: Dict):
+        """Compact host batch (token_batch_to_host) -> device batch on the copy stream while the current step runs (SURVEY.md
+        8f rank 1): the H2D copy of the token ids (~0.2 MB) and the construction of node lists and normalised adjacencies
+        (get_build_word_graphs) overlap the running step; returns a handle for step_prefetched()."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {}
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            q, d, l, kw = device_batch_from_tokens(tb, self.device)
+            ev = torch.cuda.Event()
+            ev.record()
+        e_lens = kw[K.DocLensIndices][2]
+        for t in [q, d, l, e_lens] + [v for v in kw.values() if torch.is_tensor(v)]:
+            t.record_stream(main)      # allocated on the copy stream, read by the main stream's copy into the static inputs
+        return ({"query": q, "document": d, "labels": l, "e_lens": e_lens, "event": ev}, kw)
+
     def step_prefetched(self, handle, n_real_claims: Optional[int] = None, global_claims: int = 0) -> torch.Tensor:
         """Call order for full overlap: loss = step_prefetched(h_i); h_next = prefetch(batch_{i+1}); read loss."""
         st, kw_dev = handle

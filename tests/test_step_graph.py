@@ -201,3 +201,42 @@ def test_token_batch_builds_the_same_inputs_on_the_device():
     assert torch.equal(tkw[K.Query_lens], kw[K.Query_lens])
     assert torch.equal(tkw[K.DocLensIndices][2], kw[K.DocLensIndices][2])
     assert torch.equal(tkw[K.EvidenceCountPerQuery], kw[K.EvidenceCountPerQuery])
+
+
+@pytest.mark.gpu
+def test_prefetched_token_batches_give_the_same_steps():
+    """prefetch_tokens (side-stream token H2D + device graph construction) + step_prefetched == step on the dense batch."""
+    from get_b200.ddp import FlatAdam, FlatGradAllReduce, trainable_named_parameters
+    from get_b200.model import Graph_basedSemantiStructure
+    from get_b200.step_graph import CapturedTrainStep, token_batch_to_host
+    dev = "cuda"
+    w = synthetic.get_workload("snopes", batch_claims=3, vocab=300, n_article_sources=8)
+    batches = [pad_batch(synthetic.make_batch(w, seed=s), 16) for s in (1, 2, 3)]
+
+    def run(tokens):
+        torch.manual_seed(4)
+        m = Graph_basedSemantiStructure(synthetic.match_params(w, cuda=True)).to(dev).eval()
+        named = trainable_named_parameters(m)
+        red = FlatGradAllReduce([p for _, p in named], names=[n for n, _ in named])
+        st = CapturedTrainStep(m, FlatAdam(red, lr=1e-3, weight_decay=1e-3), red)
+        losses = []
+        if tokens:
+            tbs = [token_batch_to_host(b) for b in batches]
+            nxt = st.prefetch_tokens(tbs[0])
+            for i in range(6):
+                loss = st.step_prefetched(nxt, batches[i % 3]["n_real_claims"])
+                if i + 1 < 6:
+                    nxt = st.prefetch_tokens(tbs[(i + 1) % 3])
+                losses.append(float(loss))
+        else:
+            for i in range(6):
+                b = batches[i % 3]
+                q, d, l, kw = synthetic.batch_to_torch(b, device=dev)
+                kw[K.Evd_Docs_Adj] = kw[K.Evd_Docs_Adj].float()
+                kw[K.Query_Adj] = kw[K.Query_Adj].float()
+                losses.append(float(st.step(q, d, l, kw, b["n_real_claims"])))
+        red.detach()
+        return losses
+
+    a, b = run(False), run(True)
+    assert np.allclose(a, b, rtol=0, atol=2e-6), (a, b)
