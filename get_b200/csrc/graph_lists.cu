@@ -485,51 +485,90 @@ __global__ void __launch_bounds__(GR_THREADS, 2) gather_row_kernel(const __grid_
   const uint32_t pitch = (uint32_t)HQ * 16u;
   const float4* xg = reinterpret_cast<const float4*>(p.x + row0 * H) + lane;
   const uint32_t seed = (SPILL && drop) ? p.seed_2 + __ldg(p.salt) : 0u;
+  // The loop body is instruction-issue bound, so the common case is specialised: (a) every edge of the graph sits in shared
+  // memory (nnz <= lcap: always at window 3 / 5), (b) the row is kept, so no per-edge mask test, (c) rows without edges
+  // (the pad nodes of a text, ~25 % of the rows) store constants without any conversion; row pointers advance by constant
+  // strides instead of being recomputed.
+#define GR_EDGE(J, W)                                                                                          \
+  {                                                                                                            \
+    if (!SPILL || (J) < cap) {                                                                                 \
+      const uint32_t ra = tl + (uint32_t)(J) * pitch;                                                          \
+      _Pragma("unroll") for (int u = 0; u < NQ; ++u) {                                                         \
+        if (u < NQ - 1 || last_ok) {                                                                           \
+          const float4 f = lds128f(ra + u * 512);                                                              \
+          acc[u].x = fmaf(W, f.x, acc[u].x); acc[u].y = fmaf(W, f.y, acc[u].y);                                \
+          acc[u].z = fmaf(W, f.z, acc[u].z); acc[u].w = fmaf(W, f.w, acc[u].w);                                \
+        }                                                                                                      \
+      }                                                                                                        \
+    } else {                                                                                                   \
+      /* a row beyond the tile's capacity (a text with more than `cap` distinct words): straight from global */ \
+      /* memory, the layer-2 dropout applied per gathered quad */                                              \
+      _Pragma("unroll") for (int u = 0; u < NQ; ++u) {                                                         \
+        if (u < NQ - 1 || last_ok) {                                                                           \
+          float4 f = __ldg(xg + (int64_t)(J) * HQ + u * 32);                                                   \
+          if (drop) drop_apply4(seed, (uint64_t)(row0 + (J)) * (uint64_t)H + (uint64_t)(lane + u * 32) * 4, p.thr, p.scale, f); \
+          acc[u].x = fmaf(W, f.x, acc[u].x); acc[u].y = fmaf(W, f.y, acc[u].y);                                \
+          acc[u].z = fmaf(W, f.z, acc[u].z); acc[u].w = fmaf(W, f.w, acc[u].w);                                \
+        }                                                                                                      \
+      }                                                                                                        \
+    }                                                                                                          \
+  }
+  // CTA-uniform: every list entry is in shared memory and every row a list can refer to is in the tile
+  const bool all_in_smem = m.rowptr[N] <= p.lcap && (!SPILL || n_used <= cap);
+  RowOut ro = row_out(p, row0 + warp);
+  const int64_t step_pl = (int64_t)GR_WARPS * p.ld_p;
   for (int i = warp; i < N; i += GR_WARPS) {           // warp-uniform
-    const RowOut ro = row_out(p, row0 + i);
-    float4 acc[NQ];
+    const int ea = m.rowptr[i], eb = m.rowptr[i + 1];
+    if (ea == eb && !p.accumulate) {                   // no neighbours: the row is zero
 #pragma unroll
-    for (int u = 0; u < NQ; ++u) {
-      acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.accumulate && (u < NQ - 1 || last_ok)) acc[u] = ro.f32[lane + u * 32];   // in flight during the edge loop
-    }
-    const bool dropped = masked && m.keep[i] == 0;     // a dropped node keeps only its edges to kept nodes (wrapper.py:221-225)
-    const int eb = m.rowptr[i + 1];
+      for (int u = 0; u < NQ; ++u) {
+        if (u < NQ - 1 || last_ok) {
+          const int q = lane + u * 32;
+          if (ro.f32) ro.f32[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) *reinterpret_cast<uint2*>(ro.pl[pl] + q * 4) = make_uint2(0u, 0u);
+        }
+      }
+    } else {
+      float4 acc[NQ];
+#pragma unroll
+      for (int u = 0; u < NQ; ++u) {
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.accumulate && (u < NQ - 1 || last_ok)) acc[u] = ro.f32[lane + u * 32];   // in flight during the edge loop
+      }
+      const bool dropped = masked && m.keep[i] == 0;   // a dropped node keeps only its edges to kept nodes (wrapper.py:221-225)
+      if (all_in_smem && !dropped) {
 #pragma unroll 2
-    for (int e = m.rowptr[i]; e < eb; ++e) {
-      const float2 en = list_entry(p, m, gent, e);     // one broadcast shared load
-      const int j = __float_as_int(en.x);
-      const float w = en.y;
-      if (dropped && !m.keep[j]) continue;             // warp-uniform
-      if (!SPILL || j < cap) {
-        const uint32_t ra = tl + (uint32_t)j * pitch;
+        for (int e = ea; e < eb; ++e) {
+          const float2 en = m.ent[e];                  // one broadcast shared load
+          const uint32_t ra = tl + (uint32_t)__float_as_int(en.x) * pitch;
 #pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-          if (u < NQ - 1 || last_ok) {
-            const float4 f = lds128f(ra + u * 512);
-            acc[u].x = fmaf(w, f.x, acc[u].x); acc[u].y = fmaf(w, f.y, acc[u].y);
-            acc[u].z = fmaf(w, f.z, acc[u].z); acc[u].w = fmaf(w, f.w, acc[u].w);
+          for (int u = 0; u < NQ; ++u) {
+            if (u < NQ - 1 || last_ok) {
+              const float4 f = lds128f(ra + u * 512);
+              acc[u].x = fmaf(en.y, f.x, acc[u].x); acc[u].y = fmaf(en.y, f.y, acc[u].y);
+              acc[u].z = fmaf(en.y, f.z, acc[u].z); acc[u].w = fmaf(en.y, f.w, acc[u].w);
+            }
           }
         }
       } else {
-        // a row beyond the tile's capacity (a text with more than `cap` distinct words): straight from global memory, the
-        // layer-2 dropout applied per gathered quad
-#pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-          if (u < NQ - 1 || last_ok) {
-            float4 f = __ldg(xg + (int64_t)j * HQ + u * 32);
-            if (drop) drop_apply4(seed, (uint64_t)(row0 + j) * (uint64_t)H + (uint64_t)(lane + u * 32) * 4, p.thr, p.scale, f);
-            acc[u].x = fmaf(w, f.x, acc[u].x); acc[u].y = fmaf(w, f.y, acc[u].y);
-            acc[u].z = fmaf(w, f.z, acc[u].z); acc[u].w = fmaf(w, f.w, acc[u].w);
-          }
+        for (int e = ea; e < eb; ++e) {
+          const float2 en = list_entry(p, m, gent, e);
+          const int j = __float_as_int(en.x);
+          if (dropped && !m.keep[j]) continue;         // warp-uniform
+          GR_EDGE(j, en.y)
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < NQ; ++u)
-      if (u < NQ - 1 || last_ok) store_quad<NP>(ro, lane + u * 32, acc[u]);
+      for (int u = 0; u < NQ; ++u)
+        if (u < NQ - 1 || last_ok) store_quad<NP>(ro, lane + u * 32, acc[u]);
+    }
     if (NP && lane < npq) store_pad_quad<NP>(ro, H, lane, p.pad_one != 0);
+    if (ro.f32) ro.f32 += GR_WARPS * HQ;               // next row of this warp
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) ro.pl[pl] += step_pl;
   }
+#undef GR_EDGE
 #ifdef GETB_GRAPH_TIMELINE
   if (lane == 0 && warp == GR_WARPS - 1) trow[6] = clock64() - tr0;
   __syncthreads();
