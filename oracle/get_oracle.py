@@ -235,3 +235,31 @@ def near_tie_graphs(score: Tensor, rate: float, tol: float = 1e-5) -> Tensor:
     # gap == 0 is an exact tie, which only happens among pad nodes (identical features, zero adjacency rows
     # and columns): whichever of them is kept, the refined adjacency is the same
     return (gap < tol) & (gap > 0)
+
+
+def neighbor_lists(adj: np.ndarray, transpose: bool = False):
+    """CSR restatement of a dense normalised adjacency (the operand of `adj.matmul(x)`, wrapper.py:192): (rowptr (N+1,),
+    index (nnz,), weight (nnz,), used) with rows in order and neighbours in increasing index; used = 1 + the highest
+    neighbour index (0 for an empty graph). This is the record format of get_build_neighbor_lists (include/get_b200.h);
+    sum_e weight[e] * x[index[e]] over a row's entries IS the row of adj @ x."""
+    a = np.asarray(adj)
+    if transpose:
+        a = a.T
+    rows, cols = np.nonzero(a)                              # row-major order
+    counts = np.bincount(rows, minlength=a.shape[0])
+    rowptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    used = int(cols.max()) + 1 if cols.size else 0
+    return rowptr, cols.astype(np.int64), a[rows, cols], used
+
+
+def aggregate_lists(rowptr, index, weight, x: np.ndarray, keep: Optional[np.ndarray] = None) -> np.ndarray:
+    """out[i] = sum over the entries e of row i of weight[e] * x[index[e]]; with `keep`, edges whose two endpoints are both
+    dropped are removed (the GSL mask of wrapper.py:221-225 applied per edge)."""
+    out = np.zeros((len(rowptr) - 1, x.shape[1]), dtype=np.float64)
+    for i in range(len(rowptr) - 1):
+        for e in range(rowptr[i], rowptr[i + 1]):
+            j = index[e]
+            if keep is not None and not keep[i] and not keep[j]:
+                continue
+            out[i] += float(weight[e]) * x[j].astype(np.float64)
+    return out

@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from get_b200 import ops, synthetic
+from helpers import import_oracle
 from get_b200.planes import alloc_planes
 
 pytestmark = pytest.mark.gpu
@@ -32,14 +33,14 @@ def test_lists_match_dense_adjacency(G, N, H):
     torch.cuda.synchronize()
     ent, rowptr, used = L.ent.cpu().numpy(), L.rowptr.cpu().numpy(), L.used.cpu().numpy()
     a = adj.cpu().numpy()
-    for o, dense in ((0, a), (1, a.transpose(0, 2, 1))):
+    oracle = import_oracle()
+    for o in (0, 1):
         for g in range(G):
-            nzr, nzc = np.nonzero(dense[g])                       # row-major order = CSR order
-            assert (rowptr[o, g, :N + 1] == np.concatenate([[0], np.cumsum((dense[g] != 0).sum(-1))])).all()
-            cols = ent[o, g, :len(nzc), 0].copy().view(np.int32)
-            assert (cols == nzc).all()
-            assert (ent[o, g, :len(nzc), 1] == dense[g][nzr, nzc]).all()
-            assert used[o, g] == (nzc.max() + 1 if len(nzc) else 0)
+            rp, idx, w, u = oracle.neighbor_lists(a[g], transpose=bool(o))      # the record format, restated in numpy
+            assert (rowptr[o, g, :N + 1] == rp).all()
+            assert (ent[o, g, :len(idx), 0].copy().view(np.int32) == idx).all()
+            assert (ent[o, g, :len(idx), 1] == w).all()
+            assert used[o, g] == u
 
 
 @pytest.mark.parametrize("G,N,H", [(7, 30, 300), (9, 100, 300), (3, 100, 96), (2, 200, 512), (4, 17, 24), (1, 1, 8)])

@@ -151,3 +151,27 @@ def test_oracle_matches_reference_on_a_real_snopes_batch():
     for n, g in grads.items():
         flat = g.reshape(-1)
         assert np.allclose(flat[torch.from_numpy(gold["gradidx/" + n])].numpy(), gold["gradval/" + n], atol=2e-6), n
+
+
+def test_neighbor_list_restatement_equals_dense_products_on_reference_graphs():
+    """The CSR record format of the list kernels, restated in numpy, against the reference's own graphs (convert_text +
+    _laplacian_normalize outputs in graphs.npz): adj @ x, adj^T @ x and the GSL-masked product are reproduced exactly."""
+    oracle = import_oracle()
+    d = load_golden("graphs")
+    rng = np.random.default_rng(0)
+    names = sorted({k.split("/")[0] for k in d.keys()})
+    assert names
+    for g in names:
+        adj = d[g + "/adj"].astype(np.float64)
+        n = adj.shape[0]
+        x = rng.standard_normal((n, 12))
+        keep = rng.random(n) < 0.6
+        for tr in (False, True):
+            rowptr, idx, w, used = oracle.neighbor_lists(adj, transpose=tr)
+            a = adj.T if tr else adj
+            assert rowptr[-1] == (a != 0).sum() and used == (np.nonzero(a)[1].max() + 1 if (a != 0).any() else 0)
+            assert all((np.diff(idx[rowptr[i]:rowptr[i + 1]]) > 0).all() for i in range(n))
+            assert np.allclose(oracle.aggregate_lists(rowptr, idx, w, x), a @ x, rtol=0, atol=1e-12)
+            masked = a * (keep[:, None] | keep[None, :])
+            assert np.allclose(oracle.aggregate_lists(rowptr, idx, w, x, keep), masked @ x, rtol=0, atol=1e-12)
+        assert np.allclose(adj, adj.T)          # GET graphs are symmetric: the builder writes both records in one pass
